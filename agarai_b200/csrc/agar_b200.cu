@@ -1,0 +1,313 @@
+// agar_b200.cu — C-ABI of the engine (include/agar_b200.h): handle management, launches, and the
+// host-buffer convenience call.  Built for sm_100a only (see agarai_b200/build.py).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/agar_b200.h"
+#include "../../include/agar_spec.h"
+#include "agar_kernels.cuh"
+
+using namespace agar;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& m) { g_err = m; return 1; }
+
+#define CUDA_OK(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
+    } while (0)
+
+constexpr int kThreads = 128;
+
+}  // namespace
+
+struct AgarEnv {
+    DevParams p;
+    int device = 0;
+    float* d_state = nullptr;
+    int32_t* d_events = nullptr;
+    int32_t* d_ev_counts = nullptr;
+    float* d_tab_xy = nullptr;
+    int32_t* d_tab_act = nullptr;
+    int32_t n_actions = 0;
+    size_t smem = 0;
+    int64_t launches = 0;
+    // staging for agar_step_host
+    float* d_target = nullptr; int32_t* d_act = nullptr; float* d_obs = nullptr;
+    float* d_reward = nullptr; uint8_t* d_done = nullptr;
+    cudaStream_t host_stream = nullptr;
+};
+
+namespace {
+
+size_t obs_elems(const AgarEnv* e) {
+    const AgarConfig& c = e->p.c;
+    return (size_t)c.num_arenas * c.num_agents * e->p.C * c.grid_size * c.grid_size;
+}
+
+int launch(AgarEnv* e, KArgs& a, int n_records, cudaStream_t st) {
+    a.n_records = n_records;
+    agar_step_kernel<kThreads><<<n_records, kThreads, e->smem, st>>>(e->p, a);
+    CUDA_OK(cudaGetLastError());
+    e->launches += 1;
+    return 0;
+}
+
+KArgs base_args(AgarEnv* e) {
+    KArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.state = e->d_state;
+    a.src_state = e->d_state;
+    a.events = e->d_events;
+    a.ev_counts = e->d_ev_counts;
+    return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* agar_last_error(void) { return g_err.c_str(); }
+int agar_abi_version(void) { return AGAR_ABI_VERSION; }
+
+int agar_config_default(AgarConfig* cfg) {
+    if (!cfg) return fail("cfg is NULL");
+    agar_spec_config_default(cfg);
+    return 0;
+}
+
+int agar_layout_compute(const AgarConfig* cfg, AgarLayout* out) {
+    if (!cfg || !out) return fail("NULL argument");
+    if (const char* m = agar_spec_config_check(cfg)) return fail(m);
+    agar_spec_layout(cfg, out);
+    return 0;
+}
+
+int agar_obs_channels(const AgarConfig* cfg) { return cfg ? agar_spec_obs_channels(cfg) : 0; }
+
+int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
+    if (!cfg || !out) return fail("NULL argument");
+    if (const char* m = agar_spec_config_check(cfg)) return fail(std::string("bad config: ") + m);
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail("no such CUDA device");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("libagar_b200 is built for sm_100a (B200) only");
+
+    AgarEnv* e = new (std::nothrow) AgarEnv();
+    if (!e) return fail("out of host memory");
+    e->device = device;
+    DevParams& p = e->p;
+    std::memset(&p, 0, sizeof(p));
+    p.c = *cfg;
+    agar_spec_layout(cfg, &p.L);
+    p.C = agar_spec_obs_channels(cfg);
+    p.K = p.L.num_players;
+    p.KC = p.L.cells_total;
+    const int G = cfg->grid_size;
+    const double box_d = (double)cfg->view_size / (double)G;  // features/extractors.py:19
+    p.box = (float)box_d;
+    for (int i = 0; i < G; ++i) p.oob_off[i] = (float)((double)(i - G / 2) * box_d);
+    e->smem = smem_bytes(p.L, G);
+    if (e->smem > (size_t)prop.sharedMemPerBlockOptin) {
+        delete e;
+        return fail("arena record + observation tile do not fit in shared memory (" + std::to_string(e->smem) + " B)");
+    }
+    CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    const size_t state_bytes = (size_t)cfg->num_arenas * p.L.words * sizeof(float);
+    CUDA_OK(cudaMalloc(&e->d_state, state_bytes));
+    CUDA_OK(cudaMemset(e->d_state, 0, state_bytes));
+    if (cfg->event_capacity > 0) {
+        CUDA_OK(cudaMalloc(&e->d_events, (size_t)cfg->num_arenas * cfg->event_capacity * 4 * sizeof(int32_t)));
+        CUDA_OK(cudaMalloc(&e->d_ev_counts, (size_t)cfg->num_arenas * sizeof(int32_t)));
+        CUDA_OK(cudaMemset(e->d_ev_counts, 0, (size_t)cfg->num_arenas * sizeof(int32_t)));
+    }
+    *out = e;
+    return 0;
+}
+
+int agar_destroy(AgarEnv* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaFree(e->d_state); cudaFree(e->d_events); cudaFree(e->d_ev_counts);
+    cudaFree(e->d_tab_xy); cudaFree(e->d_tab_act);
+    cudaFree(e->d_target); cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_reward); cudaFree(e->d_done);
+    if (e->host_stream) cudaStreamDestroy(e->host_stream);
+    delete e;
+    return 0;
+}
+
+int agar_get_config(const AgarEnv* e, AgarConfig* out) {
+    if (!e || !out) return fail("NULL argument");
+    *out = e->p.c;
+    return 0;
+}
+
+int agar_get_layout(const AgarEnv* e, AgarLayout* out) {
+    if (!e || !out) return fail("NULL argument");
+    *out = e->p.L;
+    return 0;
+}
+
+int agar_seed(AgarEnv* e, uint64_t seed) {
+    if (!e) return fail("env is NULL");
+    CUDA_OK(cudaSetDevice(e->device));
+    e->p.seed_lo = (uint32_t)seed;
+    e->p.seed_hi = (uint32_t)(seed >> 32);
+    // tick counters restart from 0: one strided 4-byte memset per arena record
+    CUDA_OK(cudaMemset2D(e->d_state + e->p.L.tick, (size_t)e->p.L.words * sizeof(float), 0, sizeof(int32_t),
+                         (size_t)e->p.c.num_arenas));
+    return 0;
+}
+
+int agar_reset(AgarEnv* e, const uint8_t* d_reset_mask, float* d_obs, void* stream) {
+    if (!e) return fail("env is NULL");
+    CUDA_OK(cudaSetDevice(e->device));
+    KArgs a = base_args(e);
+    a.flags = F_RESET | (d_obs ? F_OBS : 0);
+    a.reset_mask = d_reset_mask;
+    a.obs = d_obs;
+    return launch(e, a, e->p.c.num_arenas, (cudaStream_t)stream);
+}
+
+int agar_step(AgarEnv* e, const float* d_target_xy, const int32_t* d_act, float* d_obs, float* d_reward,
+              uint8_t* d_done, void* stream) {
+    if (!e) return fail("env is NULL");
+    if (!d_target_xy || !d_act || !d_reward || !d_done) return fail("agar_step: NULL action/reward/done buffer");
+    CUDA_OK(cudaSetDevice(e->device));
+    KArgs a = base_args(e);
+    a.flags = F_STEP | (d_obs ? F_OBS : 0);
+    a.target_xy = d_target_xy; a.act = d_act; a.obs = d_obs; a.reward = d_reward; a.done = d_done;
+    return launch(e, a, e->p.c.num_arenas, (cudaStream_t)stream);
+}
+
+int agar_set_action_table(AgarEnv* e, const float* h_xy, const int32_t* h_act, int32_t n) {
+    if (!e || !h_xy || !h_act) return fail("NULL argument");
+    if (n < 1 || n > 65536) return fail("n_actions out of range");
+    CUDA_OK(cudaSetDevice(e->device));
+    cudaFree(e->d_tab_xy); cudaFree(e->d_tab_act);
+    e->d_tab_xy = nullptr; e->d_tab_act = nullptr;
+    CUDA_OK(cudaMalloc(&e->d_tab_xy, (size_t)n * 2 * sizeof(float)));
+    CUDA_OK(cudaMalloc(&e->d_tab_act, (size_t)n * sizeof(int32_t)));
+    CUDA_OK(cudaMemcpy(e->d_tab_xy, h_xy, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->d_tab_act, h_act, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    e->n_actions = n;
+    return 0;
+}
+
+int agar_step_indexed(AgarEnv* e, const int32_t* d_action_index, float* d_obs, float* d_reward, uint8_t* d_done,
+                      void* stream) {
+    if (!e) return fail("env is NULL");
+    if (!e->d_tab_xy) return fail("agar_step_indexed: call agar_set_action_table first");
+    if (!d_action_index || !d_reward || !d_done) return fail("agar_step_indexed: NULL buffer");
+    CUDA_OK(cudaSetDevice(e->device));
+    KArgs a = base_args(e);
+    a.flags = F_STEP | (d_obs ? F_OBS : 0);
+    a.act_index = d_action_index; a.tab_xy = e->d_tab_xy; a.tab_act = e->d_tab_act; a.n_actions = e->n_actions;
+    a.obs = d_obs; a.reward = d_reward; a.done = d_done;
+    return launch(e, a, e->p.c.num_arenas, (cudaStream_t)stream);
+}
+
+int agar_observe(AgarEnv* e, float* d_obs, void* stream) {
+    if (!e || !d_obs) return fail("NULL argument");
+    CUDA_OK(cudaSetDevice(e->device));
+    KArgs a = base_args(e);
+    a.flags = F_OBS | F_READONLY;
+    a.obs = d_obs;
+    return launch(e, a, e->p.c.num_arenas, (cudaStream_t)stream);
+}
+
+int agar_observe_records(AgarEnv* e, const float* d_state, int32_t n_records, float* d_obs, void* stream) {
+    if (!e || !d_obs || !d_state) return fail("NULL argument");
+    if (n_records < 1) return fail("n_records must be >= 1");
+    if (((uintptr_t)d_state & 15) != 0) return fail("d_state must be 16-byte aligned");
+    CUDA_OK(cudaSetDevice(e->device));
+    KArgs a = base_args(e);
+    a.flags = F_OBS | F_READONLY;
+    a.src_state = d_state;
+    a.obs = d_obs;
+    return launch(e, a, n_records, (cudaStream_t)stream);
+}
+
+int agar_get_state(AgarEnv* e, float* d_dst, void* stream) {
+    if (!e || !d_dst) return fail("NULL argument");
+    CUDA_OK(cudaSetDevice(e->device));
+    CUDA_OK(cudaMemcpyAsync(d_dst, e->d_state, (size_t)e->p.c.num_arenas * e->p.L.words * sizeof(float),
+                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int agar_set_state(AgarEnv* e, const float* d_src, void* stream) {
+    if (!e || !d_src) return fail("NULL argument");
+    CUDA_OK(cudaSetDevice(e->device));
+    CUDA_OK(cudaMemcpyAsync(e->d_state, d_src, (size_t)e->p.c.num_arenas * e->p.L.words * sizeof(float),
+                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int agar_events(AgarEnv* e, int32_t* d_events, int32_t* d_counts, void* stream) {
+    if (!e || !d_events || !d_counts) return fail("NULL argument");
+    const int cap = e->p.c.event_capacity;
+    if (cap <= 0) return fail("event log disabled (event_capacity == 0)");
+    CUDA_OK(cudaSetDevice(e->device));
+    const size_t N = (size_t)e->p.c.num_arenas;
+    CUDA_OK(cudaMemcpyAsync(d_events, e->d_events, N * cap * 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CUDA_OK(cudaMemcpyAsync(d_counts, e->d_ev_counts, N * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, float* h_obs, float* h_reward,
+                   uint8_t* h_done) {
+    if (!e) return fail("env is NULL");
+    if (!h_target_xy || !h_act || !h_reward || !h_done) return fail("agar_step_host: NULL buffer");
+    CUDA_OK(cudaSetDevice(e->device));
+    const size_t NA = (size_t)e->p.c.num_arenas * e->p.c.num_agents;
+    if (!e->host_stream) {
+        CUDA_OK(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaMalloc(&e->d_target, NA * 2 * sizeof(float)));
+        CUDA_OK(cudaMalloc(&e->d_act, NA * sizeof(int32_t)));
+        CUDA_OK(cudaMalloc(&e->d_reward, NA * sizeof(float)));
+        CUDA_OK(cudaMalloc(&e->d_done, NA));
+    }
+    if (h_obs && !e->d_obs) CUDA_OK(cudaMalloc(&e->d_obs, obs_elems(e) * sizeof(float)));
+    cudaStream_t st = e->host_stream;
+    CUDA_OK(cudaMemcpyAsync(e->d_target, h_target_xy, NA * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(e->d_act, h_act, NA * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (int rc = agar_step(e, e->d_target, e->d_act, h_obs ? e->d_obs : nullptr, e->d_reward, e->d_done, st)) return rc;
+    if (h_obs) CUDA_OK(cudaMemcpyAsync(h_obs, e->d_obs, obs_elems(e) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(h_reward, e->d_reward, NA * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(h_done, e->d_done, NA, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int agar_gae(const float* d_reward, const float* d_value, const uint8_t* d_done, const float* d_end_value,
+             double gamma, double lam, float* d_adv, float* d_ret, int32_t T, int32_t N, void* stream) {
+    if (!d_reward) return fail("agar_gae: d_reward is NULL");
+    if (d_adv && !d_value) return fail("agar_gae: advantages need d_value");
+    if (!d_adv && !d_ret) return fail("agar_gae: nothing to compute");
+    if (T < 0 || N < 0) return fail("agar_gae: negative size");
+    if (T == 0 || N == 0) return 0;  // test/returns_test.py:15-19: empty rollouts are legal
+    const float g = (float)gamma, cgl = (float)(gamma * lam);
+    const int threads = 128, blocks = (N + threads - 1) / threads;
+    agar_gae_kernel<8><<<blocks, threads, 0, (cudaStream_t)stream>>>(d_reward, d_value, d_done, d_end_value, g, cgl,
+                                                                  d_adv, d_ret, T, N);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int64_t agar_launch_count(const AgarEnv* e) { return e ? e->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,868 @@
+// agar_kernels.cuh — device side of the B200 batched Agar.io engine (sm_100a).
+//
+// One CTA owns one arena for one env step: it stages the arena's whole state record in shared
+// memory, runs ticks_per_step ticks there, writes back only what changed and rasterises the
+// grid observations straight from shared memory with 128-bit streaming stores.  The rules are
+// those of DESIGN.md §3; the sequential definition is oracle/agar_oracle.c and the two must
+// agree bit for bit, so every float expression here is written as single IEEE operations in
+// the same order (the file is compiled with -fmad=false; sqrtf and '/' are the correctly
+// rounded forms under nvcc's default -prec-sqrt/-prec-div).
+//
+// Reference interfaces this stands in for: env.step / env.reset (ppo/train.py:164,173,
+// a2c/training.py:66,94, dqn/training.py:96,104) and GridFeatureExtractor.extract
+// (features/extractors.py:39-96).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/agar_b200.h"
+
+#define MC AGAR_MAX_CELLS
+#define NONE_I 0x7fffffff
+
+namespace agar {
+
+struct DevParams {
+    AgarConfig c;
+    AgarLayout L;
+    uint32_t seed_lo, seed_hi;
+    int C;            // observation channels
+    float box;        // (float)(view/G), the divisor of features/extractors.py:77-78
+    int K, KC;
+    float oob_off[128];  // (float)((double)(i - G/2) * (view/G)), features/extractors.py:87-91
+};
+
+struct KArgs {
+    float* state;            // [N, words] world state (library owned)
+    const float* src_state;  // records to read (== state except for observe_records)
+    const float* target_xy;  // [N,A,2]
+    const int32_t* act;      // [N,A]
+    const int32_t* act_index;  // [N,A] or null
+    const float* tab_xy;       // [n_actions,2]
+    const int32_t* tab_act;    // [n_actions]
+    int32_t n_actions;
+    float* obs;              // [N,A,C,G,G] or null
+    float* reward;           // [N,A]
+    uint8_t* done;           // [N,A]
+    const uint8_t* reset_mask;  // [N] or null (= all) — only read when F_RESET
+    int32_t* events;         // [N,cap,4]
+    int32_t* ev_counts;      // [N]
+    int32_t flags;
+    int32_t n_records;
+};
+
+enum { F_STEP = 1, F_RESET = 2, F_OBS = 4, F_READONLY = 8 };
+
+// ------------------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t& o0, uint32_t& o1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1;
+}
+
+__device__ __forceinline__ float u01(uint32_t u) { return (float)(u >> 8) * (1.0f / 16777216.0f); }
+
+__device__ __forceinline__ void rand_pos(const DevParams& p, uint32_t gid_lo, uint32_t gid_hi, uint32_t slot,
+                                         uint32_t stream, uint32_t tick, float& x, float& y) {
+    uint32_t o0, o1;
+    philox4x32_10(slot, stream, tick, gid_lo, p.seed_lo, p.seed_hi ^ gid_hi, o0, o1);
+    x = u01(o0) * p.c.arena_size;
+    y = u01(o1) * p.c.arena_size;
+}
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ------------------------------------------------------------- half-warp (one player) helpers
+// A player's 16 cell slots map to the 16 lanes of a half-warp: hmask names that half, hbase is
+// 0 or 16, slot = lane & 15.  Every lane of the half must call these together.
+
+// numpy's pairwise add-reduce over the first n (<=16) lanes of the half, see np_sum16 in the oracle
+__device__ __forceinline__ float hw_np_sum(unsigned hmask, int hbase, int slot, float a, int n) {
+    float res;
+    if (n < 8) {
+        res = 0.0f;
+        for (int i = 0; i < 7; ++i) {
+            float v = __shfl_sync(hmask, a, hbase + i);
+            if (i < n) res = res + v;
+        }
+    } else {
+        float hi = __shfl_sync(hmask, a, hbase + ((slot + 8) & 15));
+        float r = (n == 16) ? a + hi : a;
+        r = r + __shfl_xor_sync(hmask, r, 1);
+        r = r + __shfl_xor_sync(hmask, r, 2);
+        r = r + __shfl_xor_sync(hmask, r, 4);
+        res = __shfl_sync(hmask, r, hbase);
+        if (n < 16)
+            for (int i = 8; i < 15; ++i) {
+                float v = __shfl_sync(hmask, a, hbase + i);
+                if (i < n) res = res + v;
+            }
+    }
+    return res;
+}
+
+// features/extractors.py:207-212 `position` in numpy float32 evaluation order
+__device__ __forceinline__ bool hw_centroid(unsigned hmask, int hbase, int slot, float x, float y, float m,
+                                            float& cx, float& cy) {
+    unsigned alive = (__ballot_sync(hmask, m > 0.0f) >> hbase) & 0xFFFFu;
+    int n = __popc(alive);
+    if (n == 0) return false;
+    unsigned src = __fns(alive, 0, slot + 1);
+    int srcl = (slot < n) ? (int)src : 0;
+    float w = __shfl_sync(hmask, m, hbase + srcl);
+    float xs = __shfl_sync(hmask, x, hbase + srcl);
+    float ys = __shfl_sync(hmask, y, hbase + srcl);
+    float xw = xs * w, yw = ys * w;
+    float den = hw_np_sum(hmask, hbase, slot, w, n);
+    float nx = hw_np_sum(hmask, hbase, slot, xw, n);
+    float ny = hw_np_sum(hmask, hbase, slot, yw, n);
+    cx = nx / den;
+    cy = ny / den;
+    return true;
+}
+
+// butterfly 8,4,2,1 sum of the 16 slots (treesum16 in the oracle); result valid in every lane
+__device__ __forceinline__ float hw_treesum(unsigned hmask, float v) {
+    v = v + __shfl_xor_sync(hmask, v, 8);
+    v = v + __shfl_xor_sync(hmask, v, 4);
+    v = v + __shfl_xor_sync(hmask, v, 2);
+    v = v + __shfl_xor_sync(hmask, v, 1);
+    return v;
+}
+
+// ------------------------------------------------------------------------- shared memory map
+struct Smem {
+    float* rec;       // [words] the arena record
+    int32_t* reci;    // same, as int32
+    float* tile;      // [G*G] one observation channel
+    float4* list;     // [KC] alive cells (x, y, r2, gid bits), ascending gid
+    int32_t* cnt;     // [KC] per-cell counters / winners
+    float* gain;      // [KC]
+    int32_t* first;   // [KC]
+    int32_t* vwin;    // [V_pad]
+    float *Tx, *Ty, *dirx, *diry, *Cx, *Cy, *mass0;  // [64] each
+    int32_t *pact, *palive;                          // [64]
+    int32_t *oobx, *ooby;                            // [128]
+    int32_t* freefood;                               // [F_pad]
+    int32_t* sc;                                     // [16] scalars
+};
+enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT, SC_EVCOUNT, SC_RESET, SC_ALLDONE };
+
+__host__ __device__ inline size_t smem_bytes(const AgarLayout& L, int G) {
+    size_t w = 0;
+    w += (size_t)L.words;               // rec
+    w += (size_t)G * G;                 // tile
+    w += (size_t)L.cells_total * 4;     // list
+    w += (size_t)L.cells_total * 3;     // cnt, gain, first
+    w += (size_t)(L.V_pad + 4);         // vwin
+    w += 64 * 9;                        // per-player arrays
+    w += 256;                           // oobx, ooby
+    w += (size_t)(L.F_pad + 4);         // freefood
+    w += 16;                            // scalars
+    return w * 4 + 16;
+}
+
+__device__ __forceinline__ Smem carve(float* base, const AgarLayout& L, int G) {
+    Smem s;
+    float* p = base;
+    s.rec = p; s.reci = (int32_t*)p; p += L.words;           // words % 4 == 0
+    s.tile = p; p += G * G;                                  // G % 4 == 0
+    s.list = (float4*)p; p += L.cells_total * 4;
+    s.cnt = (int32_t*)p; p += L.cells_total;
+    s.gain = p; p += L.cells_total;
+    s.first = (int32_t*)p; p += L.cells_total;
+    s.vwin = (int32_t*)p; p += L.V_pad + 4;
+    s.Tx = p; p += 64; s.Ty = p; p += 64; s.dirx = p; p += 64; s.diry = p; p += 64;
+    s.Cx = p; p += 64; s.Cy = p; p += 64; s.mass0 = p; p += 64;
+    s.pact = (int32_t*)p; p += 64; s.palive = (int32_t*)p; p += 64;
+    s.oobx = (int32_t*)p; p += 128; s.ooby = (int32_t*)p; p += 128;
+    s.freefood = (int32_t*)p; p += L.F_pad + 4;
+    s.sc = (int32_t*)p; p += 16;
+    return s;
+}
+
+// -------------------------------------------------------------------------------- events
+__device__ __forceinline__ void ev_push(const DevParams& p, const KArgs& a, const Smem& s, int arena, int tick,
+                                        int type, int x, int y) {
+    int cap = p.c.event_capacity;
+    if (cap <= 0) return;
+    int i = atomicAdd(&s.sc[SC_EVCOUNT], 1);
+    if (i < cap) {
+        int4 e = make_int4(tick, type, x, y);
+        *reinterpret_cast<int4*>(a.events + ((size_t)arena * cap + i) * 4) = e;
+    }
+}
+
+// ----------------------------------------------------------------------------- sub-phases
+__device__ __forceinline__ void clear_cell(const DevParams& p, const Smem& s, int g) {
+    s.rec[p.L.cell_x + g] = 0.0f; s.rec[p.L.cell_y + g] = 0.0f; s.rec[p.L.cell_ix + g] = 0.0f;
+    s.rec[p.L.cell_iy + g] = 0.0f; s.rec[p.L.cell_m + g] = 0.0f; s.rec[p.L.cell_t + g] = 0.0f;
+}
+
+// env.reset() for one arena, in shared memory (reset_arena in the oracle)
+__device__ void reset_arena(const DevParams& p, const Smem& s, uint32_t gid_lo, uint32_t gid_hi) {
+    const AgarLayout& L = p.L;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    uint32_t tick = (uint32_t)s.reci[L.tick];
+    __syncthreads();
+    for (int i = tid; i < L.words; i += nt) s.rec[i] = 0.0f;
+    __syncthreads();
+    if (tid == 0) s.reci[L.tick] = (int32_t)tick;
+    for (int i = tid; i < L.P_pad; i += nt) {
+        float x = -1.0f, y = -1.0f;
+        if (i < p.c.num_pellets) rand_pos(p, gid_lo, gid_hi, (uint32_t)i, AGAR_STREAM_PELLET_INIT, tick, x, y);
+        s.rec[L.pellet_x + i] = x; s.rec[L.pellet_y + i] = y;
+    }
+    for (int i = tid; i < L.V_pad; i += nt) {
+        float x = -1.0f, y = -1.0f;
+        if (i < p.c.num_viruses) rand_pos(p, gid_lo, gid_hi, (uint32_t)i, AGAR_STREAM_VIRUS_INIT, tick, x, y);
+        s.rec[L.virus_x + i] = x; s.rec[L.virus_y + i] = y;
+    }
+    for (int i = tid; i < L.F_pad; i += nt) s.rec[L.food_x + i] = -1.0f;
+    for (int k = tid; k < p.K; k += nt) {
+        float x, y;
+        rand_pos(p, gid_lo, gid_hi, (uint32_t)k, AGAR_STREAM_PLAYER_SPAWN, tick, x, y);
+        s.rec[L.cell_x + k * MC] = x; s.rec[L.cell_y + k * MC] = y;
+        s.rec[L.cell_m + k * MC] = p.c.start_mass;
+    }
+    __syncthreads();
+}
+
+// warp 0: ordered list of alive cells (x, y, r2, gid); ascending gid so "first hit" == lowest gid
+__device__ __forceinline__ void build_list(const DevParams& p, const Smem& s) {
+    const AgarLayout& L = p.L;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int n = 0;
+        for (int base = 0; base < p.KC; base += 32) {
+            int g = base + lane;
+            float m = (g < p.KC) ? s.rec[L.cell_m + g] : 0.0f;
+            bool al = m > 0.0f;
+            unsigned b = __ballot_sync(0xffffffffu, al);
+            if (al)
+                s.list[n + __popc(b & ((1u << lane) - 1u))] =
+                    make_float4(s.rec[L.cell_x + g], s.rec[L.cell_y + g], m * p.c.r2_per_mass, __int_as_float(g));
+            n += __popc(b);
+        }
+        if (lane == 0) s.sc[SC_NLIST] = n;
+    }
+}
+
+// GridFeatureExtractor.extract for every agent of the arena held in s.rec
+// (features/extractors.py:39-96; oracle_grid_extract).  obs_arena points at [A,C,G,G].
+__device__ void raster_arena(const DevParams& p, const Smem& s, float* __restrict__ obs_arena) {
+    const AgarLayout& L = p.L;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int hbase = lane & 16, slot = lane & 15;
+    const unsigned hmask = 0xFFFFu << hbase;
+    const int G = p.c.grid_size, GG = G * G, A = p.c.num_agents, K = p.K;
+    const float box = p.box, arena = p.c.arena_size, view = p.c.view_size;
+    const int half = G / 2;
+
+    // centroids of all agents (half-warp per agent)
+    for (int g = tid; g < A * MC; g += nt) {
+        int k = g >> 4;
+        float cx = 0.0f, cy = 0.0f;
+        bool has = hw_centroid(hmask, hbase, slot, s.rec[L.cell_x + g], s.rec[L.cell_y + g], s.rec[L.cell_m + g], cx, cy);
+        if (slot == 0) { s.Cx[k] = cx; s.Cy[k] = cy; s.palive[k] = has ? 1 : 0; }
+    }
+    __syncthreads();
+
+    for (int a = 0; a < A; ++a) {
+        const float cx = s.Cx[a], cy = s.Cy[a];
+        const bool has = s.palive[a] != 0;
+        float* out_a = obs_arena + (size_t)a * p.C * GG;
+        // per-row / per-column out-of-bounds flags (add_out_of_bounds, features/extractors.py:84-96)
+        for (int i = tid; i < G; i += nt) {
+            float xl = p.oob_off[i] + cx, yl = p.oob_off[i] + cy;
+            s.oobx[i] = !(0.0f <= xl && xl < arena);
+            s.ooby[i] = !(0.0f <= yl && yl < arena);
+        }
+        int ch = 0;
+        for (int bit = 0; bit < 5; ++bit) {
+            const int flag = 1 << bit;
+            if (!(p.c.obs_flags & flag)) continue;
+            bool sentinel = has;
+            if (has) {
+                if (flag == AGAR_OBS_PELLETS || flag == AGAR_OBS_VIRUSES || flag == AGAR_OBS_FOODS) {
+                    // point entities: value 1 each (add_ones with len(entity) <= 2); float adds of 1.0
+                    // are exact, so shared-memory atomics give an order-independent count
+                    const float* ex; const float* ey; int n; bool marker;
+                    if (flag == AGAR_OBS_PELLETS) { ex = s.rec + L.pellet_x; ey = s.rec + L.pellet_y; n = p.c.num_pellets; marker = true; }
+                    else if (flag == AGAR_OBS_VIRUSES) { ex = s.rec + L.virus_x; ey = s.rec + L.virus_y; n = p.c.num_viruses; marker = false; }
+                    else { ex = s.rec + L.food_x; ey = s.rec + L.food_y; n = p.c.max_foods; marker = true; }
+                    for (int i = tid; i < n; i += nt) {
+                        float x = ex[i], y = ey[i];
+                        if (marker && !(x >= 0.0f)) continue;
+                        float dx = x - cx, dy = y - cy;
+                        if (fabsf(dx) > view || fabsf(dy) > view) continue;  // cannot land in the grid
+                        int gx = (int)(dx / box) + half, gy = (int)(dy / box) + half;
+                        if (0 <= gx && gx < G && 0 <= gy && gy < G) atomicAdd(&s.tile[gx * G + gy], 1.0f);
+                    }
+                } else {
+                    // cell rows: value = mass, accumulated strictly in entity order (own: slot order;
+                    // others: player order then slot order) by warp 0
+                    if (flag == AGAR_OBS_OTHERS) sentinel = K > 1;
+                    if (tid < 32) {
+                        const int g0 = (flag == AGAR_OBS_CELLS) ? a * MC : 0;
+                        const int g1 = (flag == AGAR_OBS_CELLS) ? a * MC + MC : p.KC;
+                        for (int base = g0; base < g1; base += 32) {
+                            int g = base + lane;
+                            float m = (g < g1) ? s.rec[L.cell_m + g] : 0.0f;
+                            bool ok = m > 0.0f && ((flag == AGAR_OBS_CELLS) || (g >> 4) != a);
+                            int bin = -1;
+                            if (ok) {
+                                float dx = s.rec[L.cell_x + g] - cx, dy = s.rec[L.cell_y + g] - cy;
+                                if (!(fabsf(dx) > view || fabsf(dy) > view)) {
+                                    int gx = (int)(dx / box) + half, gy = (int)(dy / box) + half;
+                                    if (0 <= gx && gx < G && 0 <= gy && gy < G) bin = gx * G + gy;
+                                }
+                            }
+                            unsigned mask = __ballot_sync(0xffffffffu, bin >= 0);
+                            while (mask) {
+                                int src = __ffs(mask) - 1;
+                                if (lane == src) s.tile[bin] = s.tile[bin] + m;
+                                __syncwarp();
+                                mask &= mask - 1;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // write the channel out with 128-bit streaming stores and re-zero the tile
+            float4* tile4 = reinterpret_cast<float4*>(s.tile);
+            float4* out4 = reinterpret_cast<float4*>(out_a + (size_t)ch * GG);
+            for (int i = tid; i < GG / 4; i += nt) {
+                float4 v = tile4[i];
+                if (sentinel) {
+                    int cell = i * 4, gx = cell / G, gy = cell - gx * G;
+                    if (s.oobx[gx]) { v.x = v.y = v.z = v.w = -1.0f; }
+                    else {
+                        if (s.ooby[gy]) v.x = -1.0f;
+                        if (s.ooby[gy + 1]) v.y = -1.0f;
+                        if (s.ooby[gy + 2]) v.z = -1.0f;
+                        if (s.ooby[gy + 3]) v.w = -1.0f;
+                    }
+                }
+                __stcs(out4 + i, v);
+                tile4[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+            __syncthreads();
+            ++ch;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------- the kernel
+// grid = number of arenas (records); block = AGAR_THREADS; dynamic smem = smem_bytes().
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) agar_step_kernel(const __grid_constant__ DevParams p,
+                                                            const __grid_constant__ KArgs a) {
+    extern __shared__ __align__(16) float smem_raw[];
+    const AgarLayout& L = p.L;
+    const AgarConfig& c = p.c;
+    const Smem s = carve(smem_raw, L, c.grid_size);
+    const int tid = threadIdx.x, nt = kThreads, lane = tid & 31;
+    const int hbase = lane & 16, slot = lane & 15;
+    const unsigned hmask = 0xFFFFu << hbase;
+    const int arena = blockIdx.x;
+    const int A = c.num_agents, K = p.K, KC = p.KC, P = c.num_pellets, V = c.num_viruses, F = c.max_foods;
+    const uint64_t gid64 = (uint64_t)(c.arena_id_base + arena);
+    const uint32_t gid_lo = (uint32_t)gid64, gid_hi = (uint32_t)(gid64 >> 32);
+    const float r2pm = c.r2_per_mass, arena_size = c.arena_size;
+    float* cx = s.rec + L.cell_x; float* cy = s.rec + L.cell_y; float* cix = s.rec + L.cell_ix;
+    float* ciy = s.rec + L.cell_iy; float* cm = s.rec + L.cell_m; float* ct = s.rec + L.cell_t;
+    float* px = s.rec + L.pellet_x; float* py = s.rec + L.pellet_y;
+    float* vx = s.rec + L.virus_x; float* vy = s.rec + L.virus_y;
+    float* fx = s.rec + L.food_x; float* fy = s.rec + L.food_y; float* fvx = s.rec + L.food_vx; float* fvy = s.rec + L.food_vy;
+    float* grec = a.state + (size_t)arena * L.words;  // write target
+
+    // ---- stage the record ----
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.src_state + (size_t)arena * L.words);
+        float4* dst = reinterpret_cast<float4*>(s.rec);
+        for (int i = tid; i < L.words / 4; i += nt) dst[i] = __ldg(src + i);
+        float4* t4 = reinterpret_cast<float4*>(s.tile);
+        for (int i = tid; i < c.grid_size * c.grid_size / 4; i += nt) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < 16) s.sc[tid] = 0;
+    }
+    __syncthreads();
+
+    bool static_dirty = false;  // whole record must be written back (after a reset)
+    if (a.flags & F_RESET) {
+        if (!a.reset_mask || a.reset_mask[arena]) { reset_arena(p, s, gid_lo, gid_hi); static_dirty = true; }
+    }
+
+    if (a.flags & F_STEP) {
+        const uint32_t tick0 = (uint32_t)s.reci[L.tick];
+        // ---- step start: mass before, bot respawn, centroids, targets ----
+        for (int g = tid; g < KC; g += nt) {
+            const int k = g >> 4;
+            float m = cm[g];
+            float mb = hw_treesum(hmask, m);
+            bool alive = __ballot_sync(hmask, m > 0.0f) != 0u;
+            if (k >= A && !alive) {  // dead bot: respawn (spawn_player in the oracle)
+                clear_cell(p, s, g);
+                if (slot == 0) {
+                    float x, y;
+                    rand_pos(p, gid_lo, gid_hi, (uint32_t)k, AGAR_STREAM_PLAYER_SPAWN, tick0, x, y);
+                    cx[g] = x; cy[g] = y; cm[g] = c.start_mass;
+                    ev_push(p, a, s, arena, 0, AGAR_EV_RESPAWN, k, 0);
+                }
+                __syncwarp(hmask);
+                m = cm[g];
+                alive = true;
+            }
+            float Cx = 0.0f, Cy = 0.0f;
+            if (alive) hw_centroid(hmask, hbase, slot, cx[g], cy[g], m, Cx, Cy);
+            if (slot == 0) {
+                s.palive[k] = alive ? 1 : 0;
+                s.Cx[k] = Cx; s.Cy[k] = Cy;
+                s.pact[k] = 0; s.Tx[k] = 0.0f; s.Ty[k] = 0.0f; s.dirx[k] = 1.0f; s.diry[k] = 0.0f;
+                if (k < A) {
+                    s.mass0[k] = mb;
+                    if (alive) {
+                        float ax, ay; int act;
+                        const size_t ia = (size_t)arena * A + k;
+                        if (a.act_index) {
+                            int idx = a.act_index[ia];
+                            idx = idx < 0 ? 0 : (idx >= a.n_actions ? a.n_actions - 1 : idx);
+                            ax = a.tab_xy[2 * idx]; ay = a.tab_xy[2 * idx + 1]; act = a.tab_act[idx];
+                        } else {
+                            ax = a.target_xy[2 * ia]; ay = a.target_xy[2 * ia + 1]; act = a.act[ia];
+                        }
+                        float n2 = ax * ax + ay * ay;
+                        if (!(n2 < INFINITY)) { ax = 0.0f; ay = 0.0f; }
+                        else if (n2 > 1.0f) { float inv = 1.0f / sqrtf(n2); ax = ax * inv; ay = ay * inv; }
+                        s.Tx[k] = Cx + ax * c.target_reach;
+                        s.Ty[k] = Cy + ay * c.target_reach;
+                        float m2 = ax * ax + ay * ay;
+                        if (m2 > 0.0f) { float inv = 1.0f / sqrtf(m2); s.dirx[k] = ax * inv; s.diry[k] = ay * inv; }
+                        act = (act == AGAR_ACT_SPLIT || act == AGAR_ACT_FEED) ? act : 0;
+                        s.pact[k] = act;
+                        if (act == AGAR_ACT_FEED) s.sc[SC_ANYFEED] = 1;
+                        if (act == AGAR_ACT_SPLIT) s.sc[SC_ANYSPLIT] = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- bots: nearest pellet in the square sense window, else roam way-point (warp per bot) ----
+        for (int k = A + (tid >> 5); k < K; k += nt >> 5) {
+            const float Cx = s.Cx[k], Cy = s.Cy[k], R = c.bot_sense_radius;
+            float best = INFINITY; int bi = NONE_I;
+            for (int i = lane; i < P; i += 32) {
+                float x = px[i];
+                if (!(x >= 0.0f)) continue;
+                float dx = x - Cx, dy = py[i] - Cy;
+                if (fabsf(dx) <= R && fabsf(dy) <= R) {
+                    float d2 = dx * dx + dy * dy;
+                    if (d2 < best) { best = d2; bi = i; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (lane == 0) {
+                if (bi != NONE_I) { s.Tx[k] = px[bi]; s.Ty[k] = py[bi]; }
+                else {
+                    uint32_t epoch = tick0 & ~(uint32_t)(c.bot_roam_period - 1);
+                    float x, y;
+                    rand_pos(p, gid_lo, gid_hi, (uint32_t)k, AGAR_STREAM_BOT_ROAM, epoch, x, y);
+                    s.Tx[k] = x; s.Ty[k] = y;
+                }
+            }
+        }
+        // ---- split: i-th eligible cell -> i-th free slot (ballot ranks inside the half-warp) ----
+        if (s.sc[SC_ANYSPLIT]) {
+            for (int g = tid; g < A * MC; g += nt) {
+                const int k = g >> 4;
+                if (s.pact[k] != AGAR_ACT_SPLIT) continue;  // uniform per half-warp
+                float m = cm[g];
+                unsigned freeb = (__ballot_sync(hmask, m == 0.0f) >> hbase) & 0xFFFFu;
+                bool elig = m >= c.split_min_mass;
+                unsigned eligb = (__ballot_sync(hmask, elig) >> hbase) & 0xFFFFu;
+                int i = __popc(eligb & ((1u << slot) - 1u));
+                if (elig && i < __popc(freeb)) {
+                    int d = k * MC + (int)__fns(freeb, 0, i + 1);
+                    float halfm = m * 0.5f;
+                    cm[g] = halfm; ct[g] = c.merge_delay;
+                    cx[d] = cx[g]; cy[d] = cy[g];
+                    cix[d] = s.dirx[k] * c.split_speed; ciy[d] = s.diry[k] * c.split_speed;
+                    cm[d] = halfm; ct[d] = c.merge_delay;
+                    ev_push(p, a, s, arena, 0, AGAR_EV_SPLIT, g, d);
+                }
+            }
+        }
+        // ---- feed: cells in gid order take free food slots in ascending order (warp 0) ----
+        if (s.sc[SC_ANYFEED] && tid < 32) {
+            int nfree = 0;
+            for (int base = 0; base < L.F_pad; base += 32) {
+                int f = base + lane;
+                bool fr = f < F && !(fx[f] >= 0.0f);
+                unsigned b = __ballot_sync(0xffffffffu, fr);
+                if (fr) s.freefood[nfree + __popc(b & ((1u << lane) - 1u))] = f;
+                nfree += __popc(b);
+            }
+            __syncwarp();
+            int used = 0;
+            for (int k = 0; k < A; ++k) {
+                if (s.pact[k] != AGAR_ACT_FEED) continue;
+                int g = k * MC + lane;
+                float m = (lane < MC) ? cm[g] : 0.0f;
+                bool elig = (lane < MC) && m >= c.feed_min_mass;
+                unsigned b = __ballot_sync(0xffffffffu, elig);
+                int rank = used + __popc(b & ((1u << lane) - 1u));
+                if (elig && rank < nfree) {
+                    int f = s.freefood[rank];
+                    float r = sqrtf(m * r2pm);
+                    cm[g] = m - c.food_mass;
+                    float off = r + c.food_spawn_gap;
+                    fx[f] = clampf(cx[g] + s.dirx[k] * off, 0.0f, arena_size);
+                    fy[f] = clampf(cy[g] + s.diry[k] * off, 0.0f, arena_size);
+                    fvx[f] = s.dirx[k] * c.feed_speed; fvy[f] = s.diry[k] * c.feed_speed;
+                    ev_push(p, a, s, arena, 0, AGAR_EV_FEED, g, f);
+                }
+                used += __popc(b);
+            }
+        }
+        __syncthreads();
+
+        for (int tk = 0; tk < c.ticks_per_step; ++tk) {
+            const uint32_t tick = tick0 + (uint32_t)tk;
+            // ---- motion ----
+            for (int g = tid; g < KC; g += nt) {
+                float m = cm[g];
+                s.cnt[g] = 0;
+                if (!(m > 0.0f)) continue;
+                const int k = g >> 4;
+                float r = sqrtf(m * r2pm);
+                float spd = c.speed_k / sqrtf(r);
+                float dx = s.Tx[k] - cx[g], dy = s.Ty[k] - cy[g];
+                float d = sqrtf(dx * dx + dy * dy);
+                float den = d > c.target_reach ? d : c.target_reach;
+                float sc = spd / den;
+                float nx = cx[g] + (dx * sc + cix[g]);
+                float ny = cy[g] + (dy * sc + ciy[g]);
+                float ix = cix[g] * c.impulse_decay, iy = ciy[g] * c.impulse_decay;
+                if (fabsf(ix) < 1e-3f && fabsf(iy) < 1e-3f) { ix = 0.0f; iy = 0.0f; }
+                cx[g] = clampf(nx, 0.0f, arena_size); cy[g] = clampf(ny, 0.0f, arena_size);
+                cix[g] = ix; ciy[g] = iy;
+                float t = ct[g];
+                if (t > 0.0f) ct[g] = t - 1.0f;
+            }
+            for (int f = tid; f < F; f += nt)
+                if (fx[f] >= 0.0f) s.sc[SC_FOODANY] = 1;
+            for (int v = tid; v < V; v += nt) s.vwin[v] = NONE_I;
+            __syncthreads();
+            build_list(p, s);
+            __syncthreads();
+            // ---- pellets: each pellet looks for the lowest-gid cell whose disc holds its centre ----
+            {
+                const int n = s.sc[SC_NLIST];
+                for (int i = tid; i < P; i += nt) {
+                    float x = px[i];
+                    if (!(x >= 0.0f)) continue;
+                    float y = py[i];
+                    for (int j = 0; j < n; ++j) {
+                        float4 cl = s.list[j];
+                        float dx = x - cl.x, dy = y - cl.y;
+                        if (dx * dx + dy * dy < cl.z) {
+                            int g = __float_as_int(cl.w);
+                            atomicAdd(&s.cnt[g], 1);
+                            ev_push(p, a, s, arena, tk, AGAR_EV_PELLET_EATEN, g, i);
+                            float nx = -1.0f, ny = -1.0f;
+                            if (c.pellet_regen) rand_pos(p, gid_lo, gid_hi, (uint32_t)i, AGAR_STREAM_PELLET_RESPAWN, tick, nx, ny);
+                            px[i] = nx; py[i] = ny;
+                            if (!(a.flags & F_READONLY)) { grec[L.pellet_x + i] = nx; grec[L.pellet_y + i] = ny; }
+                            break;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            for (int g = tid; g < KC; g += nt) {
+                int n = s.cnt[g];
+                if (n) { cm[g] = cm[g] + (float)n * c.pellet_mass; s.cnt[g] = 0; }
+            }
+            // ---- foods: move, then eaten like pellets ----
+            if (s.sc[SC_FOODANY]) {  // block-uniform (written before the last barrier)
+                __syncthreads();
+                build_list(p, s);
+                __syncthreads();
+                const int n = s.sc[SC_NLIST];
+                for (int f = tid; f < F; f += nt) {
+                    float x = fx[f];
+                    if (!(x >= 0.0f)) continue;
+                    float nx = x + fvx[f], ny = fy[f] + fvy[f];
+                    float ux = fvx[f] * c.food_decay, uy = fvy[f] * c.food_decay;
+                    if (fabsf(ux) < 1e-3f && fabsf(uy) < 1e-3f) { ux = 0.0f; uy = 0.0f; }
+                    x = clampf(nx, 0.0f, arena_size); float y = clampf(ny, 0.0f, arena_size);
+                    fx[f] = x; fy[f] = y; fvx[f] = ux; fvy[f] = uy;
+                    for (int j = 0; j < n; ++j) {
+                        float4 cl = s.list[j];
+                        float dx = x - cl.x, dy = y - cl.y;
+                        if (dx * dx + dy * dy < cl.z) {
+                            int g = __float_as_int(cl.w);
+                            atomicAdd(&s.cnt[g], 1);
+                            ev_push(p, a, s, arena, tk, AGAR_EV_FOOD_EATEN, g, f);
+                            fx[f] = -1.0f; fy[f] = 0.0f; fvx[f] = 0.0f; fvy[f] = 0.0f;
+                            break;
+                        }
+                    }
+                }
+                __syncthreads();
+                for (int g = tid; g < KC; g += nt) {
+                    int n2 = s.cnt[g];
+                    if (n2) { cm[g] = cm[g] + (float)n2 * c.food_mass; s.cnt[g] = 0; }
+                }
+                if (tid == 0) s.sc[SC_FOODANY] = 0;
+            }
+            __syncthreads();
+            // ---- viruses: heavy cells claim the viruses inside them (atomicMin = lowest gid) ----
+            if (V > 0) {
+                for (int g = tid; g < KC; g += nt) {
+                    float m = cm[g];
+                    s.first[g] = NONE_I;
+                    if (!(m >= c.virus_pop_mass)) continue;
+                    float r2 = m * r2pm, x = cx[g], y = cy[g];
+                    for (int v = 0; v < V; ++v) {
+                        float dx = vx[v] - x, dy = vy[v] - y;
+                        if (dx * dx + dy * dy < r2) { atomicMin(&s.vwin[v], g); s.sc[SC_ANYVHIT] = 1; }
+                    }
+                }
+                __syncthreads();
+                if (s.sc[SC_ANYVHIT]) {
+                    for (int g = tid; g < KC; g += nt) {
+                        if (!(cm[g] >= c.virus_pop_mass)) continue;
+                        for (int v = 0; v < V; ++v)
+                            if (s.vwin[v] == g) { s.first[g] = v; break; }
+                    }
+                    __syncthreads();
+                    // pops: one thread per player walks its slots in order (free slots are consumed
+                    // sequentially inside a player, exactly as the oracle does)
+                    for (int k = tid; k < K; k += nt) {
+                        for (int sl = 0; sl < MC; ++sl) {
+                            const int g = k * MC + sl;
+                            const int v = s.first[g];
+                            if (v == NONE_I) continue;
+                            float m1 = cm[g] + c.virus_mass;
+                            int freeslot[MC]; int nfree = 0;
+                            for (int q = 0; q < MC; ++q)
+                                if (cm[k * MC + q] == 0.0f) freeslot[nfree++] = q;
+                            int np = nfree < c.pop_pieces ? nfree : c.pop_pieces;
+                            ev_push(p, a, s, arena, tk, AGAR_EV_VIRUS_POP, g, v);
+                            if (np > 0) {
+                                const float DX[16] = AGAR_DIR16_X; const float DY[16] = AGAR_DIR16_Y;
+                                float keep = m1 * 0.5f;
+                                float piece = (m1 - keep) / (float)np;
+                                cm[g] = keep; ct[g] = c.merge_delay;
+                                for (int j = 0; j < np; ++j) {
+                                    int d = k * MC + freeslot[j];
+                                    cx[d] = cx[g]; cy[d] = cy[g];
+                                    cix[d] = DX[j] * c.pop_speed; ciy[d] = DY[j] * c.pop_speed;
+                                    cm[d] = piece; ct[d] = c.merge_delay;
+                                    ev_push(p, a, s, arena, tk, AGAR_EV_POP_PIECE, g, d);
+                                }
+                            } else {
+                                cm[g] = m1;
+                            }
+                            float nx, ny;
+                            rand_pos(p, gid_lo, gid_hi, (uint32_t)v, AGAR_STREAM_VIRUS_RESPAWN, tick, nx, ny);
+                            vx[v] = nx; vy[v] = ny;
+                            if (!(a.flags & F_READONLY)) { grec[L.virus_x + v] = nx; grec[L.virus_y + v] = ny; }
+                        }
+                    }
+                    __syncthreads();
+                    if (tid == 0) s.sc[SC_ANYVHIT] = 0;
+                }
+            }
+            // ---- cell eats cell (different players) on the pre-phase snapshot ----
+            if (K > 1) {
+                __syncthreads();
+                build_list(p, s);
+                for (int g = tid; g < KC; g += nt) { s.cnt[g] = NONE_I; s.gain[g] = 0.0f; }
+                __syncthreads();
+                const int n = s.sc[SC_NLIST];
+                for (int j = tid; j < KC; j += nt) {
+                    float mj = cm[j];
+                    if (!(mj > 0.0f)) continue;
+                    const float need = mj * c.eat_ratio, x = cx[j], y = cy[j];
+                    const int kj = j >> 4;
+                    for (int q = 0; q < n; ++q) {
+                        float4 cl = s.list[q];
+                        int i = __float_as_int(cl.w);
+                        if ((i >> 4) == kj) continue;
+                        float dx = x - cl.x, dy = y - cl.y;
+                        if (dx * dx + dy * dy < cl.z && cm[i] >= need) { s.cnt[j] = i; s.sc[SC_ANYEAT] = 1; break; }
+                    }
+                }
+                __syncthreads();
+                if (s.sc[SC_ANYEAT]) {
+                    if (tid < 32) {  // gains added in ascending prey order (float sum order is part of the spec)
+                        for (int base = 0; base < KC; base += 32) {
+                            int j = base + lane;
+                            int w = (j < KC) ? s.cnt[j] : NONE_I;
+                            unsigned mask = __ballot_sync(0xffffffffu, w != NONE_I);
+                            while (mask) {
+                                int src = __ffs(mask) - 1;
+                                if (lane == src) {
+                                    s.gain[w] = s.gain[w] + cm[j];
+                                    ev_push(p, a, s, arena, tk, AGAR_EV_CELL_EATEN, w, j);
+                                }
+                                __syncwarp();
+                                mask &= mask - 1;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    for (int g = tid; g < KC; g += nt) {
+                        if (s.cnt[g] != NONE_I) clear_cell(p, s, g);
+                        else if (s.gain[g] > 0.0f) cm[g] = cm[g] + s.gain[g];
+                    }
+                    if (tid == 0) s.sc[SC_ANYEAT] = 0;
+                }
+                __syncthreads();
+            }
+            // ---- merge own cells whose timers ran out (half-warp per player, shuffles) ----
+            for (int g = tid; g < KC; g += nt) {
+                const float m = cm[g], t = ct[g], x = cx[g], y = cy[g];
+                const bool can = m > 0.0f && t == 0.0f;
+                unsigned canb = (__ballot_sync(hmask, can) >> hbase) & 0xFFFFu;
+                if (__popc(canb) < 2) continue;  // uniform per half-warp
+                const float r2 = m * r2pm;
+                int root = slot;
+                for (int q = 0; q < MC - 1; ++q) {
+                    float xa = __shfl_sync(hmask, x, hbase + q), ya = __shfl_sync(hmask, y, hbase + q);
+                    float ra = __shfl_sync(hmask, r2, hbase + q);
+                    if (can && root == slot && q < slot && ((canb >> q) & 1u)) {
+                        float dx = x - xa, dy = y - ya;
+                        float rr = ra > r2 ? ra : r2;
+                        if (dx * dx + dy * dy < rr) root = q;  // partner = lowest qualifying slot below
+                    }
+                }
+                // follow partners down to the final survivor (partner < slot, so 4 jumps suffice)
+#pragma unroll
+                for (int it = 0; it < 4; ++it) root = __shfl_sync(hmask, root, hbase + root);
+                unsigned merged = (__ballot_sync(hmask, root != slot) >> hbase) & 0xFFFFu;
+                if (merged == 0u) continue;
+                float acc = m;
+                for (int q = 1; q < MC; ++q) {
+                    float mq = __shfl_sync(hmask, m, hbase + q);
+                    int rq = __shfl_sync(hmask, root, hbase + q);
+                    if (rq == slot && q != slot) acc = acc + mq;
+                }
+                if (root != slot) {
+                    ev_push(p, a, s, arena, tk, AGAR_EV_MERGE, (g & ~15) + root, g);
+                    clear_cell(p, s, g);
+                } else if (acc != m) {
+                    cm[g] = acc;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- rewards / dones ----
+        for (int g = tid; g < A * MC; g += nt) {
+            const int k = g >> 4;
+            float m = cm[g];
+            float after = hw_treesum(hmask, m);
+            bool alive = __ballot_sync(hmask, m > 0.0f) != 0u;
+            if (slot == 0) {
+                int was = s.reci[L.agent_done + k];
+                float rw = was ? 0.0f : after - s.mass0[k];
+                if (!was && !alive) {
+                    s.reci[L.agent_done + k] = 1;
+                    ev_push(p, a, s, arena, c.ticks_per_step, AGAR_EV_DEATH, k, 0);
+                }
+                int d = s.reci[L.agent_done + k];
+                a.reward[(size_t)arena * A + k] = rw;
+                a.done[(size_t)arena * A + k] = (uint8_t)d;
+                if (!d) s.sc[SC_ALLDONE] = 1;  // at least one agent still playing
+            }
+        }
+        if (tid == 0) {
+            s.reci[L.tick] = (int32_t)(tick0 + (uint32_t)c.ticks_per_step);
+            s.reci[L.episode_steps] += 1;
+        }
+        __syncthreads();
+        if (c.auto_reset && !s.sc[SC_ALLDONE]) { reset_arena(p, s, gid_lo, gid_hi); static_dirty = true; }
+        if (c.event_capacity > 0 && tid == 0) a.ev_counts[arena] = s.sc[SC_EVCOUNT];
+    }
+
+    // ---- write back ----
+    if (!(a.flags & F_READONLY) && (a.flags & (F_STEP | F_RESET))) {
+        const int w0 = static_dirty ? 0 : L.dyn_begin;  // dyn_begin % 4 == 0
+        const float4* src = reinterpret_cast<const float4*>(s.rec);
+        float4* dst = reinterpret_cast<float4*>(grec);
+        for (int i = w0 / 4 + tid; i < L.words / 4; i += nt) dst[i] = src[i];
+    }
+    // ---- observations ----
+    if ((a.flags & F_OBS) && a.obs) {
+        const int GG = c.grid_size * c.grid_size;
+        raster_arena(p, s, a.obs + (size_t)arena * A * p.C * GG);
+    }
+}
+
+// -------------------------------------------------------------------------------- GAE
+// rl.gae / rl.make_returns (rl/__init__.py:94-159; numpy statement rl/test.py:12-30) over a
+// time-major [T,N] rollout buffer: one thread per column, reverse scan over t with the loads of
+// U steps issued before the dependent chain so that enough bytes are in flight.
+template <int U>
+__global__ void __launch_bounds__(128) agar_gae_kernel(const float* __restrict__ r, const float* __restrict__ v,
+                                                      const uint8_t* __restrict__ done,
+                                                      const float* __restrict__ end_value, float g, float cgl,
+                                                      float* __restrict__ adv, float* __restrict__ ret, int T, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float a_next = 0.0f;
+    float g_next = end_value ? end_value[n] : 0.0f;
+    float v_next = (adv != nullptr) ? __ldcs(v + (size_t)T * N + n) : 0.0f;
+    for (int t1 = T; t1 > 0; t1 -= U) {
+        float rr[U], vv[U];
+        uint8_t dd[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t1 - 1 - u;
+            const bool ok = t >= 0;
+            const size_t i = (size_t)(ok ? t : 0) * N + n;
+            rr[u] = ok ? __ldcs(r + i) : 0.0f;
+            vv[u] = (ok && adv) ? __ldcs(v + i) : 0.0f;
+            dd[u] = (ok && done) ? __ldcs(done + i) : (uint8_t)0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t1 - 1 - u;
+            if (t < 0) break;
+            const size_t i = (size_t)t * N + n;
+            const bool cut = dd[u] != 0;
+            if (adv) {
+                float vn = cut ? 0.0f : v_next;
+                float delta = (rr[u] + g * vn) - vv[u];
+                float av = (t == T - 1 || cut) ? delta : delta + cgl * a_next;
+                __stcs(adv + i, av);
+                a_next = av;
+                v_next = vv[u];
+            }
+            if (ret) {
+                float gn = cut ? 0.0f : g_next;
+                float G_t = rr[u] + g * gn;
+                __stcs(ret + i, G_t);
+                g_next = G_t;
+            }
+        }
+    }
+}
+
+}  // namespace agar

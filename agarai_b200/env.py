@@ -1,0 +1,331 @@
+"""Host-side mirror of the reference's env interface on top of the C-ABI CUDA library.
+
+`BatchedAgarioEnv` is N arenas stepped by one kernel launch, with torch CUDA tensors in and out
+(zero-copy: the library writes straight into them).  `GymCompatEnv` is the per-arena view with
+the exact calling convention of the reference's call sites:
+
+    env = gym.make(id, **kwargs)          configuration/__init__.py:45-73, ppo/train.py:361-372
+    obs = env.reset()                     ppo/train.py:164, a2c/training.py:66, dqn/training.py:96
+    obs, rewards, dones, info = env.step(actions)      ppo/train.py:173, a2c/training.py:94
+    env.observation_space.shape, env.action_space, env.render(), env.close()
+
+PyTorch is used for device memory and streams only; all compute is in libagar_b200.so and there
+is no fallback path: without the library (or without a GPU) construction raises.
+"""
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .actions import ActionConfig, ppo_action_table
+
+OBS_PELLETS, OBS_CELLS, OBS_OTHERS, OBS_VIRUSES, OBS_FOODS = 1, 2, 4, 8, 16
+
+# gym ids the reference uses (configuration/__init__.py:38-42, dqn/hyperparameters.py:89)
+GYM_IDS = ("agario-grid-v0",)
+_UNSUPPORTED_IDS = ("agario-ram-v0", "agario-screen-v0", "agario-full-v0")
+
+# `difficulty` only selects defaults in the original package; explicit kwargs win
+_DIFFICULTY_DEFAULTS = {
+    "normal": dict(num_pellets=1000, num_viruses=25, num_bots=25),
+    "empty": dict(num_pellets=1000, num_viruses=0, num_bots=0),
+    "trivial": dict(num_pellets=1000, num_viruses=0, num_bots=0),
+}
+
+
+class Box:
+    """Minimal picklable stand-in for gym.spaces.Box (observation_space / action_space are sent
+    through pipes by a2c/remote_environment.py:78-81, so they must pickle)."""
+
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+
+    def __repr__(self):
+        return f"Box({self.low}, {self.high}, {self.shape}, {np.dtype(self.dtype).name})"
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = n
+        self.shape = ()
+
+    def __repr__(self):
+        return f"Discrete({self.n})"
+
+
+class TupleSpace:
+    def __init__(self, spaces):
+        self.spaces = tuple(spaces)
+
+    def __repr__(self):
+        return f"Tuple{self.spaces}"
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def config_from_gym_kwargs(num_envs=1, **kw) -> "_lib.AgarConfig":
+    """Maps the reference's gym.make kwargs (configuration/__init__.py:53-71; a2c/train.py:17-64;
+    old style dqn/train.py:57-67) onto an AgarConfig.  Unknown keys raise like gym would; any
+    AgarConfig field may also be passed directly to override this build's rule constants."""
+    kw = dict(kw)
+    difficulty = str(kw.pop("difficulty", "normal")).lower()
+    if difficulty not in _DIFFICULTY_DEFAULTS:
+        raise ValueError(f"unknown difficulty {difficulty!r}")
+    fields = dict(_DIFFICULTY_DEFAULTS[difficulty])
+    kw.pop("multi_agent", None)  # always multi-agent capable; the compat view handles A == 1
+    if "frames_per_step" in kw:  # old-style name (dqn/train.py:58)
+        kw.setdefault("ticks_per_step", kw.pop("frames_per_step"))
+    num_frames = int(kw.pop("num_frames", 1))
+    if num_frames != 1:
+        raise ValueError("num_frames > 1 is not supported (environment.proto:44 default is 1)")
+    flags = 0
+    for key, bit in (("observe_pellets", OBS_PELLETS), ("observe_cells", OBS_CELLS),
+                     ("observe_others", OBS_OTHERS), ("observe_viruses", OBS_VIRUSES),
+                     ("observe_foods", OBS_FOODS)):
+        default = key != "observe_foods"  # environment.proto:51-54 defaults are all true
+        if bool(kw.pop(key, default)):
+            flags |= bit
+    fields["obs_flags"] = flags
+    for key in ("num_agents", "ticks_per_step", "num_pellets", "num_viruses", "num_bots", "grid_size"):
+        if key in kw:
+            fields[key] = int(kw.pop(key))
+    if "arena_size" in kw:
+        fields["arena_size"] = float(kw.pop("arena_size"))
+    if "pellet_regen" in kw:
+        fields["pellet_regen"] = int(bool(kw.pop("pellet_regen")))
+    fields["num_arenas"] = int(num_envs)
+    fields.update(kw)  # remaining keys must be AgarConfig fields (default_config raises otherwise)
+    return _lib.default_config(**fields)
+
+
+class BatchedAgarioEnv:
+    """N independent arenas on one GPU behind the reference's env interface.
+
+    step(target_xy[N,A,2] float32 cuda, act[N,A] int32 cuda) -> (obs[N,A,C,G,G], reward[N,A],
+    done[N,A] uint8, info).  Returned tensors are freshly allocated unless `out_obs` is given,
+    because callers keep observations for a whole episode (rollout/multi_rollout.py:42-44).
+    """
+
+    metadata = {"render.modes": []}
+
+    def __init__(self, cfg: "_lib.AgarConfig", device=None, seed: int = 0, action_config: ActionConfig = None):
+        self._h = None
+        self._L = _lib.lib()
+        if not torch.cuda.is_available():
+            raise _lib.AgarError("BatchedAgarioEnv needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = C.c_void_p()
+        _lib.check(self._L.agar_create(C.byref(cfg), self.device.index or 0, C.byref(h)))
+        self._h = h
+        self.cfg = _lib.AgarConfig()
+        _lib.check(self._L.agar_get_config(self._h, C.byref(self.cfg)))
+        self.layout = _lib.AgarLayout()
+        _lib.check(self._L.agar_get_layout(self._h, C.byref(self.layout)))
+        self.num_envs, self.num_agents = self.cfg.num_arenas, self.cfg.num_agents
+        self.channels = self._L.agar_obs_channels(C.byref(self.cfg))
+        G = self.cfg.grid_size
+        self.obs_shape = (self.num_envs, self.num_agents, self.channels, G, G)
+        # per-agent spaces, as the reference's consumers read them (dqn/qn.py:50 takes shape[0] as
+        # channels => CHW, which is also GridFeatureExtractor.shape, features/extractors.py:31)
+        self.observation_space = Box(-1.0, np.inf, (self.channels, G, G))
+        self.action_space = TupleSpace((Box(-1.0, 1.0, (2,)), Discrete(3)))
+        self.action_config = action_config or ActionConfig()
+        self.set_action_table(*ppo_action_table(self.action_config))
+        self.seed(seed)
+
+    # ---- lifecycle -----------------------------------------------------------------------
+    def close(self):
+        if self._h is not None:
+            self._L.agar_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def seed(self, seed: int):
+        _lib.check(self._L.agar_seed(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1))))
+        return [seed]
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _new_obs(self):
+        return torch.empty(self.obs_shape, dtype=torch.float32, device=self.device)
+
+    # ---- reference interface --------------------------------------------------------------
+    def reset(self, mask: Optional[torch.Tensor] = None, out_obs: Optional[torch.Tensor] = None):
+        obs = self._new_obs() if out_obs is None else out_obs
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self._L.agar_reset(self._h, _ptr(mask), _ptr(obs), self._stream()))
+        return obs
+
+    def _outs(self, out_obs, want_obs):
+        obs = (self._new_obs() if out_obs is None else out_obs) if want_obs else None
+        reward = torch.empty((self.num_envs, self.num_agents), dtype=torch.float32, device=self.device)
+        done = torch.empty((self.num_envs, self.num_agents), dtype=torch.uint8, device=self.device)
+        return obs, reward, done
+
+    def step(self, target_xy: torch.Tensor, act: torch.Tensor, out_obs=None, want_obs=True):
+        t = target_xy.to(device=self.device, dtype=torch.float32).contiguous()
+        a = act.to(device=self.device, dtype=torch.int32).contiguous()
+        if t.numel() != self.num_envs * self.num_agents * 2 or a.numel() != self.num_envs * self.num_agents:
+            raise ValueError("step: actions must be [num_envs, num_agents, 2] and [num_envs, num_agents]")
+        obs, reward, done = self._outs(out_obs, want_obs)
+        _lib.check(self._L.agar_step(self._h, _ptr(t), _ptr(a), _ptr(obs), _ptr(reward), _ptr(done), self._stream()))
+        return obs, reward, done, {}
+
+    def set_action_table(self, xy: np.ndarray, act: np.ndarray):
+        xy = np.ascontiguousarray(xy, np.float32)
+        act = np.ascontiguousarray(act, np.int32)
+        _lib.check(self._L.agar_set_action_table(self._h, xy.ctypes.data_as(C.c_void_p),
+                                                 act.ctypes.data_as(C.c_void_p), len(act)))
+        self.num_actions = len(act)
+
+    def step_discrete(self, action_index: torch.Tensor, out_obs=None, want_obs=True):
+        """env.step(vmap(action_converter)(indices)) of ppo/train.py:172-173 in one launch."""
+        idx = action_index.to(device=self.device, dtype=torch.int32).contiguous()
+        if idx.numel() != self.num_envs * self.num_agents:
+            raise ValueError("step_discrete: indices must be [num_envs, num_agents]")
+        obs, reward, done = self._outs(out_obs, want_obs)
+        _lib.check(self._L.agar_step_indexed(self._h, _ptr(idx), _ptr(obs), _ptr(reward), _ptr(done), self._stream()))
+        return obs, reward, done, {}
+
+    def observe(self, out_obs=None):
+        obs = self._new_obs() if out_obs is None else out_obs
+        _lib.check(self._L.agar_observe(self._h, _ptr(obs), self._stream()))
+        return obs
+
+    def observe_records(self, state: torch.Tensor):
+        """Rasterise state snapshots ([n, layout.words] float32) kept instead of observations."""
+        s = state.to(device=self.device, dtype=torch.float32).contiguous()
+        n = s.shape[0]
+        G = self.cfg.grid_size
+        obs = torch.empty((n, self.num_agents, self.channels, G, G), dtype=torch.float32, device=self.device)
+        _lib.check(self._L.agar_observe_records(self._h, _ptr(s), n, _ptr(obs), self._stream()))
+        return obs
+
+    def render(self, mode="human"):
+        return None  # dqn/training.py:106 calls it every step; there is nothing to draw headless
+
+    # ---- state / events (parity tests, checkpoint-resume) ----------------------------------
+    def get_state(self) -> torch.Tensor:
+        s = torch.empty((self.num_envs, self.layout.words), dtype=torch.float32, device=self.device)
+        _lib.check(self._L.agar_get_state(self._h, _ptr(s), self._stream()))
+        return s
+
+    def set_state(self, state: torch.Tensor):
+        s = state.to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(s.shape) != (self.num_envs, self.layout.words):
+            raise ValueError("set_state: wrong shape")
+        _lib.check(self._L.agar_set_state(self._h, _ptr(s), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()  # `s` may be a temporary
+
+    def events(self):
+        cap = self.cfg.event_capacity
+        ev = torch.zeros((self.num_envs, max(cap, 1), 4), dtype=torch.int32, device=self.device)
+        cnt = torch.zeros((self.num_envs,), dtype=torch.int32, device=self.device)
+        _lib.check(self._L.agar_events(self._h, _ptr(ev), _ptr(cnt), self._stream()))
+        return ev, cnt
+
+    def step_host(self, target_xy: np.ndarray, act: np.ndarray, obs: Optional[np.ndarray],
+                  reward: np.ndarray, done: np.ndarray):
+        """agar_step_host: numpy (ideally pinned) buffers in and out, copies inside."""
+        for arr, dt in ((target_xy, np.float32), (act, np.int32), (reward, np.float32), (done, np.uint8)):
+            if arr.dtype != dt or not arr.flags.c_contiguous:
+                raise ValueError("step_host: wrong dtype or non-contiguous buffer")
+        if obs is not None and (obs.dtype != np.float32 or not obs.flags.c_contiguous or obs.size != int(np.prod(self.obs_shape))):
+            raise ValueError("step_host: bad obs buffer")
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        _lib.check(self._L.agar_step_host(self._h, vp(target_xy), vp(act), vp(obs), vp(reward), vp(done)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.agar_launch_count(self._h))
+
+
+class GymCompatEnv:
+    """One arena of a BatchedAgarioEnv with the reference's calling convention.
+
+    Multi-agent (`num_agents` > 1 or multi_agent=True): `step(actions)` takes a list of
+    `(np.ndarray[2], int)` (ppo/train.py:172-173, a2c/train.py:79) and returns
+    `(obs list, rewards array, dones array, info)`; dones works as a boolean mask
+    (ppo/train.py:192) and with all() (:166).  Single-agent (DQN): `step((x, y, act))` returns
+    `(obs, float reward, bool done, info)` (dqn/training.py:103-125).  Observations are fresh
+    numpy arrays each step (callers keep them, rollout/multi_rollout.py:42-44); a done agent's
+    observation is all zeros where the reference extractor would give None
+    (features/extractors.py:42)."""
+
+    def __init__(self, env: BatchedAgarioEnv, multi_agent: bool = True):
+        if env.num_envs != 1:
+            raise ValueError("GymCompatEnv wraps a single-arena BatchedAgarioEnv (num_envs=1)")
+        self.env = env
+        self.multi_agent = multi_agent
+        self.observation_space = env.observation_space
+        self.action_space = env.action_space
+        A = env.num_agents
+        # pinned staging so the per-step copies are single async DMA transfers
+        self._t = torch.zeros((1, A, 2), dtype=torch.float32).pin_memory()
+        self._a = torch.zeros((1, A), dtype=torch.int32).pin_memory()
+        self._obs = torch.zeros(env.obs_shape, dtype=torch.float32).pin_memory()
+        self._r = torch.zeros((1, A), dtype=torch.float32).pin_memory()
+        self._d = torch.zeros((1, A), dtype=torch.uint8).pin_memory()
+
+    def seed(self, seed):
+        return self.env.seed(seed)
+
+    def _obs_out(self, obs_np):
+        if self.multi_agent:
+            return [obs_np[0, i].copy() for i in range(self.env.num_agents)]
+        return obs_np[0, 0].copy()
+
+    def reset(self):
+        obs = self.env.reset()
+        return self._obs_out(obs.cpu().numpy())
+
+    def step(self, actions):
+        A = self.env.num_agents
+        if self.multi_agent:
+            if len(actions) != A:
+                raise ValueError(f"expected {A} actions, got {len(actions)}")
+            for i, (xy, act) in enumerate(actions):
+                self._t[0, i, 0], self._t[0, i, 1] = float(xy[0]), float(xy[1])
+                self._a[0, i] = int(act)
+        else:
+            x, y, act = actions
+            self._t[0, 0, 0], self._t[0, 0, 1] = float(x), float(y)
+            self._a[0, 0] = int(act)
+        self.env.step_host(self._t.numpy(), self._a.numpy(), self._obs.numpy(), self._r.numpy(), self._d.numpy())
+        obs = self._obs_out(self._obs.numpy())
+        if self.multi_agent:
+            return obs, self._r.numpy()[0].copy(), self._d.numpy()[0].astype(bool), {}
+        return obs, float(self._r[0, 0]), bool(self._d[0, 0]), {}
+
+    def render(self, mode="human"):
+        return None
+
+    def close(self):
+        self.env.close()
+
+
+def make(env_id: str = "agario-grid-v0", num_envs: int = 1, device=None, seed: int = 0,
+         action_config: ActionConfig = None, gym_compat: Optional[bool] = None, **kwargs):
+    """gym.make(env_id, **kwargs) for the batched engine.  With num_envs == 1 (and gym_compat not
+    False) the reference-shaped per-arena view is returned; otherwise the batched tensor env."""
+    if env_id in _UNSUPPORTED_IDS:
+        raise NotImplementedError(f"{env_id}: only the grid observation family is on the accelerated path")
+    if env_id not in GYM_IDS:
+        raise ValueError(f"unknown env id {env_id!r}")
+    multi_agent = bool(kwargs.get("multi_agent", True))
+    cfg = config_from_gym_kwargs(num_envs=num_envs, **kwargs)
+    env = BatchedAgarioEnv(cfg, device=device, seed=seed, action_config=action_config)
+    if gym_compat is None:
+        gym_compat = num_envs == 1
+    return GymCompatEnv(env, multi_agent=multi_agent) if gym_compat else env
