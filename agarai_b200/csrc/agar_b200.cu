@@ -295,11 +295,11 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
 
 int agar_gae(const float* d_reward, const float* d_value, const uint8_t* d_done, const float* d_end_value,
              double gamma, double lam, float* d_adv, float* d_ret, int32_t T, int32_t N, void* stream) {
+    if (T < 0 || N < 0) return fail("agar_gae: negative size");
+    if (T == 0 || N == 0) return 0;  // test/returns_test.py:15-19: empty rollouts are legal
     if (!d_reward) return fail("agar_gae: d_reward is NULL");
     if (d_adv && !d_value) return fail("agar_gae: advantages need d_value");
     if (!d_adv && !d_ret) return fail("agar_gae: nothing to compute");
-    if (T < 0 || N < 0) return fail("agar_gae: negative size");
-    if (T == 0 || N == 0) return 0;  // test/returns_test.py:15-19: empty rollouts are legal
     const float g = (float)gamma, cgl = (float)(gamma * lam);
     const int threads = 128, blocks = (N + threads - 1) / threads;
     agar_gae_kernel<8><<<blocks, threads, 0, (cudaStream_t)stream>>>(d_reward, d_value, d_done, d_end_value, g, cgl,

@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s including the grid observation (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            # this build (CUDA, C-ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
+
+Workload (BASELINE.json configs[1]): 4096 arenas per GPU, 1 agent + 25 bots + 25 viruses, 1000
+pellets, arena 500, ticks_per_step 4, observation 3x64x64 float32, random policy over the PPO
+action set with split and feed.  One "step" = one env.step of every arena on every GPU = one
+kernel launch per GPU.  Arenas never interact, so N GPUs = N independent shards (weak scaling,
+no collective on the data path); RNG is keyed by global arena id.
+
+`value`   device-resident: action indices already in HBM, observations written to HBM.
+`e2e`     the same step through agar_step_host: actions from pinned host memory, observations,
+          rewards and dones copied back to pinned host memory inside the timed region.
+`roofline` algorithmic bytes per env-step x arenas per launch / launch duration.
+`cpu_baseline` the CPU oracle (a port: the reference's simulator is an absent external package)
+          on this box's host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ARENAS_PER_GPU = 4096
+WORLD = dict(num_agents=1, num_bots=25, num_viruses=25, num_pellets=1000, arena_size=500.0, ticks_per_step=4,
+             grid_size=64, obs_flags=7, pellet_regen=1, auto_reset=1, max_foods=64)
+METRIC = "env_steps_per_sec_incl_grid_obs"
+UNIT = "env-steps/s"
+
+
+def algorithmic_bytes_per_env_step(w=WORLD):
+    """compulsory HBM traffic of one env step (state touched once, obs written)."""
+    P, V, F, A = w["num_pellets"], w["num_viruses"], w["max_foods"], w["num_agents"]
+    K = A + w["num_bots"]
+    C = bin(w["obs_flags"]).count("1")
+    G = w["grid_size"]
+    return 8 * P + 12 * V + 2 * 24 * K * 16 + 2 * 16 * F + A * (12 + 5) + 32 + A * C * G * G * 4
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm(arenas, steps, warmup, nthreads, seed=0):
+    """Times the CPU oracle (oracle/agar_oracle.c) on `arenas` arenas of the bench world."""
+    import numpy as np
+    from oracle import oracle as O
+    import agarai_b200.actions as act_mod
+    cfg = O.default_config(num_arenas=arenas, **WORLD)
+    env = O.OracleEnv(cfg, seed=seed, nthreads=nthreads)
+    obs = env.reset()
+    xy_tab, act_tab = act_mod.ppo_action_table(act_mod.ActionConfig(8, 1, True, True))
+    rng = np.random.default_rng(seed)
+    times = []
+    for i in range(warmup + steps):
+        idx = rng.integers(0, len(act_tab), size=(arenas, 1))
+        t0 = time.perf_counter()
+        env.step(xy_tab[idx], act_tab[idx], out=obs)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    env.close()
+    return arenas * len(times) / sum(times), sum(times) / len(times)
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores.  The reference's own
+    simulator (gym_agario) is an external package that is not available, so this arm runs the
+    oracle port, multi-threaded over arenas (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 512
+    value, sec = cpu_arm(sample, args.steps, args.warmup, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: 1 agent + 25 bots + 25 viruses, 1000 pellets, arena 500, obs 3x64x64 f32",
+                   "arenas_per_step": sample, **WORLD},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} arenas x {args.steps} steps (of the {ARENAS_PER_GPU}-arena workload), "
+                                   "oracle/agar_oracle.c with one pthread per core"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import agarai_b200 as ab
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    N = args.arenas
+    ac = ab.ActionConfig(8, 1, True, True)
+    cfg = ab.default_config(num_arenas=N, arena_id_base=rank * N, **WORLD)
+    env = ab.BatchedAgarioEnv(cfg, device=dev, seed=args.seed, action_config=ac)
+    K, W = args.steps, max(args.warmup, 3)
+    gen = torch.Generator(device=dev); gen.manual_seed(args.seed + rank)
+    idx = torch.randint(0, env.num_actions, (K + W, N, 1), generator=gen, device=dev, dtype=torch.int32)
+    obs = [torch.empty(env.obs_shape, dtype=torch.float32, device=dev) for _ in range(2)]
+    env.reset(out_obs=obs[0])
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(W):
+        env.step_discrete(idx[i], out_obs=obs[i & 1])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = env.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        _, rew, done, _ = env.step_discrete(idx[W + i], out_obs=obs[i & 1])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = env.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * N * K / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers through agar_step_host (H2D actions, D2H obs/reward/done inside) ----
+    xy_tab, act_tab = ab.ppo_action_table(ac)
+    Ke = max(2, min(K, args.e2e_steps))
+    h_idx = idx[W:W + Ke].cpu().numpy()[..., 0]
+    h_xy = torch.from_numpy(np.ascontiguousarray(xy_tab[h_idx][:, :, None, :])).pin_memory()   # [Ke,N,1,2]
+    h_act = torch.from_numpy(np.ascontiguousarray(act_tab[h_idx][:, :, None])).pin_memory()    # [Ke,N,1]
+    h_obs = torch.empty(env.obs_shape, dtype=torch.float32).pin_memory()
+    h_rew = torch.empty((N, 1), dtype=torch.float32).pin_memory()
+    h_done = torch.empty((N, 1), dtype=torch.uint8).pin_memory()
+    env.step_host(h_xy[0].numpy(), h_act[0].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        env.step_host(h_xy[i].numpy(), h_act[i].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())
+    torch.cuda.synchronize(dev)
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * Ke / float(te.item())
+    h2d = N * 1 * (8 + 4)
+    d2h = h_obs.numel() * 4 + N * 1 * (4 + 1)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        B = algorithmic_bytes_per_env_step()
+        launch_s = (ms_max * 1e-3) / max(launches, 1)
+        achieved = B * N / launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: 4096 arenas/GPU, 1 agent + 25 bots + 25 viruses, 1000 pellets, arena 500, "
+                                   "obs 3x64x64 f32, random policy over 25 actions (8 dirs, split, feed)",
+                       "arenas_per_gpu": N, "l2": "no flush needed: each step streams the 79 MB state and writes a "
+                                                  "201 MB observation buffer (2 alternate) > 126 MB L2", **WORLD},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": Ke, "api": "agar_step_host (pinned host buffers; obs D2H every step)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "agar_step_kernel", "bytes_per_env_step": B,
+                         "env_steps_per_launch": N, "launch_us": launch_s * 1e6, "peak_source": peak_src},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sample = 512
+            _, sec = cpu_arm(sample, 1, 1, cores)        # size the sample for ~10-20 s of CPU work
+            steps_cpu = int(max(3, min(200, 12.0 / max(sec, 1e-3))))
+            v, sec = cpu_arm(sample, steps_cpu, 1, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{sample} arenas x {steps_cpu} steps of the same world, "
+                                              "oracle/agar_oracle.c, one pthread per core"}
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--arenas", type=int, default=ARENAS_PER_GPU, help="arenas per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

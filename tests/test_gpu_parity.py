@@ -1,0 +1,329 @@
+"""GPU parity: the CUDA engine, called through the C-ABI, against the CPU oracle on the same
+seeds and actions.  Bit-exact on everything: state words, observations, rewards, dones and the
+event multiset (the CUDA build uses -fmad=false and the oracle -ffp-contract=off, so float
+results are identical IEEE single operations; the 1e-5 relative bar of the north star is met
+with zero difference)."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+f32 = np.float32
+
+
+def _fields(cfg):
+    return {name: getattr(cfg, name) for name, _ in type(cfg)._fields_}
+
+
+def make_pair(oracle, seed=0, **kw):
+    import agarai_b200 as ab
+    ocfg = oracle.default_config(**kw)
+    gcfg = ab.default_config(**_fields(ocfg))
+    genv = ab.BatchedAgarioEnv(gcfg, seed=seed)
+    oenv = oracle.OracleEnv(ocfg, seed=seed, nthreads=8)
+    L = genv.layout
+    for name, _ in type(L)._fields_:
+        assert getattr(L, name) == getattr(oenv.L, name), name
+    return genv, oenv
+
+
+def random_actions(rng, N, A, acts=(0, 1, 2), p_act=0.3):
+    k = rng.integers(0, 9, size=(N, A))
+    th = 2 * np.pi * ((k - 1) % 8) / 8
+    mag = rng.choice([1.0, 0.5, 1.7], size=(N, A))  # 1.7 exercises the unit-disc clamp
+    xy = np.where(k[..., None] == 0, 0, np.stack([np.cos(th), np.sin(th)], -1) * mag[..., None]).astype(f32)
+    act = np.where(rng.random((N, A)) < p_act, rng.choice(acts, size=(N, A)), 0).astype(np.int32)
+    return xy, act
+
+
+def sorted_events(ev, cnt, cap):
+    out = []
+    for n in range(ev.shape[0]):
+        assert cnt[n] <= cap, "event log overflow: raise event_capacity in the test"
+        e = ev[n, :cnt[n]]
+        out.append(e[np.lexsort(e.T[::-1])] if len(e) else e)
+    return out
+
+
+def assert_same_state(genv, oenv, where=""):
+    gs = genv.get_state().cpu().numpy().view(np.int32)
+    os_ = oenv.get_state().view(np.int32)
+    if not np.array_equal(gs, os_):
+        bad = np.argwhere(gs != os_)
+        L = genv.layout
+        names = sorted(((getattr(L, n), n) for n, _ in type(L)._fields_ if n not in ("words", "dyn_begin", "dyn_end", "num_players", "cells_total", "P_pad", "V_pad", "F_pad", "A_pad")))
+        arena, word = bad[0]
+        field = [n for o, n in names if o <= word][-1]
+        raise AssertionError(f"{where}: state differs at {len(bad)} words; first arena {arena} word {word} ({field}+{word - getattr(L, field)}): gpu={gs[arena, word].view(f32) if False else gs[arena, word]} oracle={os_[arena, word]}")
+
+
+def lockstep(genv, oenv, steps, rng, acts=(0, 1, 2), p_act=0.3, check_events=True):
+    N, A = genv.num_envs, genv.num_agents
+    cap = genv.cfg.event_capacity
+    g_obs = genv.reset().cpu().numpy()
+    o_obs = oenv.reset()
+    assert np.array_equal(g_obs, o_obs), "reset observation"
+    assert_same_state(genv, oenv, "after reset")
+    counts = np.zeros(16, np.int64)
+    for t in range(steps):
+        xy, act = random_actions(rng, N, A, acts, p_act)
+        g_o, g_r, g_d, _ = genv.step(torch.from_numpy(xy).cuda(), torch.from_numpy(act).cuda())
+        o_o, o_r, o_d = oenv.step(xy, act)
+        assert_same_state(genv, oenv, f"step {t}")
+        assert np.array_equal(g_r.cpu().numpy().view(np.int32), o_r.view(np.int32)), f"rewards step {t}"
+        assert np.array_equal(g_d.cpu().numpy(), o_d), f"dones step {t}"
+        assert np.array_equal(g_o.cpu().numpy().view(np.int32), o_o.view(np.int32)), f"observations step {t}"
+        if cap > 0 and check_events:
+            ge, gc = genv.events(); oe, oc = oenv.events()
+            ge, gc = ge.cpu().numpy(), gc.cpu().numpy()
+            assert np.array_equal(gc, oc), f"event counts step {t}"
+            for a_, b_ in zip(sorted_events(ge, gc, cap), sorted_events(oe, oc, cap)):
+                assert np.array_equal(a_, b_), f"event trace step {t}"
+                for e in a_:
+                    counts[e[1]] += 1
+    return counts
+
+
+def test_cfg1_single_agent_pellets_only_1000_steps(oracle):
+    """BASELINE configs[0]: single-agent pellets-only arena, 4 envs, random policy, 1000-step
+    seeded rollout; full trace compare."""
+    genv, oenv = make_pair(oracle, seed=1, num_arenas=4, event_capacity=64,
+                           obs_flags=7)  # pellets, cells, others: 3x64x64
+    counts = lockstep(genv, oenv, 1000, np.random.default_rng(0), acts=(0,), p_act=0.0)
+    assert counts[1] > 20  # pellets were eaten
+    genv.close()
+
+
+def test_cfg2_bots_viruses_split_feed(oracle):
+    """BASELINE configs[1] world (bots + viruses, arena 500, split/feed) at a test-sized N."""
+    genv, oenv = make_pair(oracle, seed=2, num_arenas=6, num_bots=25, num_viruses=25, arena_size=500.0,
+                           event_capacity=512, obs_flags=7)
+    counts = lockstep(genv, oenv, 300, np.random.default_rng(1))
+    assert counts[1] > 1000 and counts[4] > 0  # pellets and cell-eats happened
+    genv.close()
+
+
+def test_dense_small_arena_all_event_types(oracle):
+    """Small crowded arena with low thresholds so that every rule fires often: split, feed, food
+    eaten, virus pop, cell eaten, merge, death, bot respawn, auto-reset."""
+    genv, oenv = make_pair(oracle, seed=3, num_arenas=8, num_agents=4, num_bots=6, num_viruses=6, num_pellets=400,
+                           max_foods=16, arena_size=120.0, view_size=100.0, grid_size=32, obs_flags=31,
+                           event_capacity=1024, auto_reset=1, start_mass=40.0, merge_delay=12.0,
+                           virus_mass=30.0, virus_pop_mass=60.0, speed_k=6.0, pop_pieces=5)
+    counts = lockstep(genv, oenv, 400, np.random.default_rng(2), p_act=0.5)
+    for ev in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10):
+        assert counts[ev] > 0, f"event type {ev} never fired: {counts}"
+    genv.close()
+
+
+def test_cfg4_sixteen_agents_split_merge(oracle):
+    """BASELINE configs[3] world: 16 agents per arena with split/merge (ppo.textproto:4-23)."""
+    genv, oenv = make_pair(oracle, seed=4, num_arenas=3, num_agents=16, event_capacity=512, obs_flags=7,
+                           start_mass=30.0, merge_delay=20.0)
+    counts = lockstep(genv, oenv, 150, np.random.default_rng(3), acts=(0, 1), p_act=0.4)
+    assert counts[6] > 0 and counts[5] > 0
+    genv.close()
+
+
+def test_no_regen_pellets_run_out(oracle):
+    genv, oenv = make_pair(oracle, seed=5, num_arenas=2, num_pellets=60, arena_size=40.0, pellet_regen=0,
+                           view_size=30.0, grid_size=16, event_capacity=128, speed_k=5.0)
+    lockstep(genv, oenv, 200, np.random.default_rng(4), acts=(0,), p_act=0.0)
+    L = genv.layout
+    px = genv.get_state().cpu().numpy()[:, L.pellet_x:L.pellet_x + 60]
+    assert (px < 0).sum() > 10
+    genv.close()
+
+
+def test_ragged_sizes_and_masked_reset(oracle):
+    """P, V, F not multiples of 4, odd player count, reset of a subset of arenas."""
+    genv, oenv = make_pair(oracle, seed=6, num_arenas=5, num_agents=3, num_bots=2, num_pellets=333, num_viruses=7,
+                           max_foods=9, arena_size=90.0, view_size=64.0, grid_size=8, obs_flags=27, event_capacity=256,
+                           start_mass=35.0, ticks_per_step=3)
+    rng = np.random.default_rng(5)
+    lockstep(genv, oenv, 40, rng)
+    mask = np.array([1, 0, 0, 1, 0], np.uint8)
+    g_obs = genv.reset(mask=torch.from_numpy(mask)).cpu().numpy()
+    o_obs = oenv.reset(mask=mask)
+    assert np.array_equal(g_obs, o_obs)
+    assert_same_state(genv, oenv, "masked reset")
+    xy, act = random_actions(rng, 5, 3)
+    genv.step(torch.from_numpy(xy).cuda(), torch.from_numpy(act).cuda()); oenv.step(xy, act)
+    assert_same_state(genv, oenv, "step after masked reset")
+    genv.close()
+
+
+def test_sharding_invariance_and_state_roundtrip(oracle):
+    """arena n of an 8-arena handle == arena 0 of a handle created with arena_id_base=n, and
+    get_state -> set_state into a fresh handle continues identically (checkpoint/resume)."""
+    import agarai_b200 as ab
+    kw = dict(num_agents=2, num_bots=2, num_viruses=3, arena_size=150.0, obs_flags=15)
+    big = ab.BatchedAgarioEnv(ab.default_config(num_arenas=8, **kw), seed=11)
+    part = ab.BatchedAgarioEnv(ab.default_config(num_arenas=3, arena_id_base=5, **kw), seed=11)
+    big.reset(); part.reset()
+    rng = np.random.default_rng(6)
+    for t in range(30):
+        xy, act = random_actions(rng, 8, 2)
+        txy, tact = torch.from_numpy(xy).cuda(), torch.from_numpy(act).cuda()
+        ob, rb, db, _ = big.step(txy, tact)
+        op, rp, dp, _ = part.step(txy[5:], tact[5:])
+        assert torch.equal(ob[5:], op) and torch.equal(rb[5:], rp) and torch.equal(db[5:], dp)
+    resumed = ab.BatchedAgarioEnv(ab.default_config(num_arenas=8, **kw), seed=11)
+    resumed.set_state(big.get_state())
+    xy, act = random_actions(rng, 8, 2)
+    txy, tact = torch.from_numpy(xy).cuda(), torch.from_numpy(act).cuda()
+    o1, r1, d1, _ = big.step(txy, tact); o2, r2, d2, _ = resumed.step(txy, tact)
+    assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(big.get_state(), resumed.get_state())
+    for e in (big, part, resumed):
+        e.close()
+
+
+def test_step_discrete_equals_table_lookup(oracle):
+    """agar_step_indexed == agar_step on the decoded table rows (ppo/action_conversion.py)."""
+    import agarai_b200 as ab
+    ac = ab.ActionConfig(8, 2, True, True)
+    cfgkw = dict(num_arenas=4, num_agents=2, start_mass=40.0)
+    a = ab.BatchedAgarioEnv(ab.default_config(**cfgkw), seed=1, action_config=ac)
+    b = ab.BatchedAgarioEnv(ab.default_config(**cfgkw), seed=1, action_config=ac)
+    a.reset(); b.reset()
+    xy, act = ab.ppo_action_table(ac)
+    assert len(act) == ab.action_size(ac) == 1 + 16 + 16
+    rng = np.random.default_rng(7)
+    for t in range(40):
+        idx = rng.integers(0, len(act), size=(4, 2))
+        oa, ra, da, _ = a.step_discrete(torch.from_numpy(idx).cuda())
+        ob, rb, db, _ = b.step(torch.from_numpy(xy[idx]).cuda(), torch.from_numpy(act[idx]).cuda())
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    a.close(); b.close()
+
+
+def test_raster_matches_reference_golden(oracle):
+    """agar_observe_records on hand-built records vs the outputs recorded from the reference's
+    GridFeatureExtractor (features/extractors.py:39-96): integer counts and sentinels bit-exact."""
+    import agarai_b200 as ab
+    from test_oracle_golden import check_obs_against_reference, load_grid_cases
+    for c in load_grid_cases():
+        K = int(c["K"]); P, V, F = len(c["pellets"]), len(c["viruses"]), len(c["foods"])
+        cfg = ab.default_config(num_arenas=1, num_agents=1, num_bots=K - 1, num_pellets=P, num_viruses=V, max_foods=F,
+                                grid_size=int(c["G"]), view_size=float(c["view"]), arena_size=float(c["arena"]),
+                                obs_flags=int(c["flags"]))
+        env = ab.BatchedAgarioEnv(cfg)
+        L = env.layout
+        rec = np.zeros((1, L.words), f32)
+        rec[0, L.pellet_x:L.pellet_x + L.P_pad] = -1; rec[0, L.food_x:L.food_x + L.F_pad] = -1
+        rec[0, L.pellet_x:L.pellet_x + P] = c["pellets"][:, 0]; rec[0, L.pellet_y:L.pellet_y + P] = c["pellets"][:, 1]
+        rec[0, L.virus_x:L.virus_x + V] = c["viruses"][:, 0]; rec[0, L.virus_y:L.virus_y + V] = c["viruses"][:, 1]
+        rec[0, L.food_x:L.food_x + F] = c["foods"][:, 0]; rec[0, L.food_y:L.food_y + F] = c["foods"][:, 1]
+        rec[0, L.cell_x:L.cell_x + K * 16] = c["cell_x"]; rec[0, L.cell_y:L.cell_y + K * 16] = c["cell_y"]
+        rec[0, L.cell_m:L.cell_m + K * 16] = c["cell_m"]
+        got = env.observe_records(torch.from_numpy(rec).cuda()).cpu().numpy()[0, 0]
+        check_obs_against_reference(got, c)
+        ogot, _ = oracle.grid_extract(int(c["G"]), float(c["view"]), float(c["arena"]), int(c["flags"]), 0, K,
+                                      c["pellets"], c["viruses"], c["foods"], c["cell_x"], c["cell_y"], c["cell_m"])
+        assert np.array_equal(got.view(np.int32), ogot.view(np.int32))  # and bit-equal to the oracle, masses too
+        env.close()
+
+
+def test_gae_matches_oracle_and_reference_golden(oracle):
+    import agarai_b200 as ab
+    z = np.load(os.path.join(GOLD, "gae_golden.npz"))
+    r, v = torch.from_numpy(z["r"]).cuda(), torch.from_numpy(z["v"]).cuda()
+    for n in range(r.shape[1]):  # per-column hyper-parameters, as recorded from rl/test.py's numpy statements
+        g, l = float(z["gamma"][n]), float(z["lam"][n])
+        adv, ret = ab.gae_and_returns(r[:, n:n + 1].contiguous(), v[:, n:n + 1].contiguous(), g, l)
+        assert np.array_equal(adv.cpu().numpy()[:, 0], z["adv"][:, n])
+        assert np.array_equal(ret.cpu().numpy()[:, 0], z["ret0"][:, n])
+    rng = np.random.default_rng(8)
+    for T, N in ((1, 1), (3, 5), (128, 1000), (513, 257), (7, 4099)):
+        rr = rng.normal(size=(T, N)).astype(f32); vv = rng.normal(size=(T + 1, N)).astype(f32)
+        dd = (rng.random((T, N)) < 0.05).astype(np.uint8); ev = rng.normal(size=N).astype(f32)
+        for done, end in ((None, None), (dd, ev)):
+            adv, ret = ab.gae_and_returns(torch.from_numpy(rr).cuda(), torch.from_numpy(vv).cuda(), 0.75, 0.1,
+                                          dones=None if done is None else torch.from_numpy(done).cuda(),
+                                          end_value=None if end is None else torch.from_numpy(end).cuda())
+            oadv, oret = oracle.gae(rr, vv, 0.75, 0.1, done=done, end_value=end)
+            assert np.array_equal(adv.cpu().numpy().view(np.int32), oadv.view(np.int32)), (T, N)
+            assert np.array_equal(ret.cpu().numpy().view(np.int32), oret.view(np.int32)), (T, N)
+    # rl/test.py:59-81 known answers through the CUDA path
+    r3 = torch.tensor([[0.0], [3.0], [0.0]], device="cuda")
+    for gamma in (1.0, 0.5, 0.0):
+        a = ab.gae(r3, torch.zeros(4, 1, device="cuda"), gamma, 0.0)
+        assert a[:, 0].tolist() == [0.0, 3.0, 0.0]
+        a = ab.gae(r3, torch.tensor([[0.0], [0.0], [0.0], [7.0]], device="cuda"), gamma, 0.0)
+        assert a[:, 0].tolist() == [0.0, 3.0, 7 * gamma]
+    # test/returns_test.py:15-19: empty rollout keeps its length
+    assert ab.make_returns(torch.zeros(0, 3, device="cuda"), 1.0).shape == (0, 3)
+
+
+def test_gym_compat_view_matches_reference_call_sites(oracle):
+    """The loop shape of ppo/train.py:156-197 on the compat view: list-of-(xy, act) actions in,
+    (obs list, rewards, dones mask, info) out; single-agent (x, y, act) form of dqn/training.py."""
+    import agarai_b200 as ab
+    env = ab.make("agario-grid-v0", num_agents=3, multi_agent=True, difficulty="empty", ticks_per_step=4,
+                  arena_size=200, num_pellets=200, num_viruses=0, num_bots=0, pellet_regen=True, grid_size=32,
+                  num_frames=1, observe_cells=True, observe_others=True, observe_pellets=True,
+                  observe_viruses=False, seed=5)
+    assert env.observation_space.shape == (3, 32, 32)
+    conv = ab.ActionConverter.ppo(ab.ActionConfig(8, 1))
+    obs = env.reset()
+    assert len(obs) == 3 and obs[0].shape == (3, 32, 32)
+    dones = [False] * 3
+    kept = []
+    for i in range(20):
+        if all(dones): break
+        actions = [conv(1 + (i + a) % 8) for a in range(3)]
+        next_obs, rewards, next_dones, _ = env.step(actions)
+        kept.append(obs)
+        assert rewards.shape == (3,) and next_dones.dtype == bool
+        values = np.ones(3); values[next_dones] = 0.0  # boolean-mask use, ppo/train.py:192
+        obs, dones = next_obs, next_dones
+    assert not np.shares_memory(kept[0][0], kept[1][0])
+    env.close()
+    env1 = ab.make("agario-grid-v0", multi_agent=False, difficulty="empty", frames_per_step=4, arena_size=45,
+                   num_pellets=30, num_viruses=0, num_bots=0, pellet_regen=True, grid_size=128, view_size=30.0,
+                   observe_viruses=False)
+    o = env1.reset()
+    o, r, d, _ = env1.step((0.5, -0.5, 0))
+    assert o.shape == (3, 128, 128) and isinstance(r, float) and isinstance(d, bool)
+    env1.render(); env1.close()
+
+
+def test_large_batch_properties(oracle):
+    """Full-size property checks (BASELINE configs[1] N=4096): every reward equals the change of
+    the agent's total mass, dones are consistent with empty cell rows, pellets stay in the arena,
+    and a spot-check of 16 arenas against the oracle stepping from the same state."""
+    import agarai_b200 as ab
+    kw = dict(num_bots=25, num_viruses=25, arena_size=500.0, obs_flags=7, auto_reset=0)
+    N = 4096
+    env = ab.BatchedAgarioEnv(ab.default_config(num_arenas=N, **kw), seed=9)
+    env.reset()
+    L = env.layout
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    for t in range(12):
+        idx = torch.randint(0, env.num_actions, (N, 1), generator=g, device="cuda", dtype=torch.int32)
+        m0 = env.get_state()[:, L.cell_m:L.cell_m + 16].sum(1)
+        s_before = env.get_state() if t == 11 else None
+        obs, rew, done, _ = env.step_discrete(idx)
+        st = env.get_state()
+        m1 = st[:, L.cell_m:L.cell_m + 16].sum(1)
+        assert torch.allclose(rew[:, 0], m1 - m0, rtol=1e-5, atol=1e-3)
+        assert torch.equal(done[:, 0] != 0, m1 == 0)
+        px = st[:, L.pellet_x:L.pellet_x + 1000]
+        assert (px >= 0).all() and (px < 500.0).all()
+        assert (obs[:, 0, 0] >= -1).all() and obs.shape == (N, 1, 3, 64, 64)
+    # spot check: oracle continues 16 arenas from the GPU's state before the last step
+    sel = np.arange(0, N, N // 16)[:16]
+    xy_tab, act_tab = ab.ppo_action_table(env.action_config)
+    for n in sel:
+        ocfg = oracle.default_config(num_arenas=1, arena_id_base=int(n), **kw)
+        oenv = oracle.OracleEnv(ocfg, seed=9)
+        oenv.set_state(s_before[n:n + 1].cpu().numpy())
+        i = int(idx[n, 0])
+        o_o, o_r, o_d = oenv.step(xy_tab[i][None, None], act_tab[i][None, None])
+        assert np.array_equal(oenv.get_state().view(np.int32), st[n:n + 1].cpu().numpy().view(np.int32))
+        assert np.array_equal(o_o[0], obs[n].cpu().numpy()) and o_r[0, 0] == float(rew[n, 0])
+    env.close()
