@@ -119,6 +119,7 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
     const int G = cfg->grid_size;
     const double box_d = (double)cfg->view_size / (double)G;  // features/extractors.py:19
     p.box = (float)box_d;
+    p.hash_inv = (float)HASH_W / cfg->arena_size;
     for (int i = 0; i < G; ++i) p.oob_off[i] = (float)((double)(i - G / 2) * box_d);
     e->smem = smem_bytes(p.L, G);
     if (e->smem > (size_t)prop.sharedMemPerBlockOptin) {

@@ -29,6 +29,7 @@ struct DevParams {
     int C;            // observation channels
     float box;        // (float)(view/G), the divisor of features/extractors.py:77-78
     int K, KC;
+    float hash_inv;   // HASH_W / arena_size: pellet bin index = (int)(coordinate * hash_inv)
     float oob_off[128];  // (float)((double)(i - G/2) * (view/G)), features/extractors.py:87-91
 };
 
@@ -138,34 +139,55 @@ __device__ __forceinline__ float hw_treesum(unsigned hmask, float v) {
 }
 
 // ------------------------------------------------------------------------- shared memory map
+// Pellet hash: HASH_W x HASH_W uniform grid over the arena, built by counting sort once per step
+// (and again only if more than EXTRA_CAP pellets respawned since).  It lives in the same shared
+// memory as the observation tile, which is only needed after the last tick.
+#define HASH_W 16
+#define HASH_BINS (HASH_W * HASH_W)
+#define EXTRA_CAP 64
+
 struct Smem {
     float* rec;       // [words] the arena record
     int32_t* reci;    // same, as int32
-    float* tile;      // [G*G] one observation channel
-    float4* list;     // [KC] alive cells (x, y, r2, gid bits), ascending gid
-    int32_t* cnt;     // [KC] per-cell counters / winners
+    float* tile;      // [G*G] one observation channel            (union with the hash below)
+    int32_t* hstart;  // [HASH_BINS+1] first sorted position of each bin
+    int32_t* hcur;    // [HASH_BINS]   counting-sort cursors
+    int32_t* pwin;    // [P_pad]       winner cell of each pellet this tick (atomicMin)
+    uint16_t* sorted; // [P_pad]       pellet ids in bin order
+    uint16_t* hits;   // [P_pad]       pellets claimed this tick
+    uint16_t* extras; // [EXTRA_CAP]   pellets respawned since the hash was built
+    int32_t* list;    // [KC] gids of the alive cells (unordered)
+    int32_t* cnt;     // [KC] pellets / foods eaten this tick
+    int32_t* eater;   // [KC] lowest-gid cell that eats this one (NONE_I between uses)
     float* gain;      // [KC]
-    int32_t* first;   // [KC]
+    int32_t* first;   // [KC] first virus won by the cell
     int32_t* vwin;    // [V_pad]
     float *Tx, *Ty, *dirx, *diry, *Cx, *Cy, *mass0;  // [64] each
-    int32_t *pact, *palive;                          // [64]
+    int32_t *pact, *palive, *pmask;                  // [64]
     int32_t *oobx, *ooby;                            // [128]
     int32_t* freefood;                               // [F_pad]
-    int32_t* sc;                                     // [16] scalars
+    int32_t* sc;                                     // [16] scalars + [32] list-membership bitmask
 };
-enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT, SC_EVCOUNT, SC_RESET, SC_ALLDONE };
+enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT, SC_EVCOUNT, SC_RESET, SC_ALLDONE,
+       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_ANYMULTI_START };
+
+__host__ __device__ inline size_t union_words(const AgarLayout& L, int G) {
+    size_t hash = (size_t)(HASH_BINS + 1 + 3) + HASH_BINS + L.P_pad + (size_t)L.P_pad / 2 * 2 + EXTRA_CAP / 2 + 8;
+    size_t tile = (size_t)G * G;
+    size_t u = hash > tile ? hash : tile;
+    return (u + 3) & ~(size_t)3;
+}
 
 __host__ __device__ inline size_t smem_bytes(const AgarLayout& L, int G) {
     size_t w = 0;
     w += (size_t)L.words;               // rec
-    w += (size_t)G * G;                 // tile
-    w += (size_t)L.cells_total * 4;     // list
-    w += (size_t)L.cells_total * 3;     // cnt, gain, first
+    w += union_words(L, G);             // tile | hash
+    w += (size_t)L.cells_total * 5;     // list, cnt, eater, gain, first
     w += (size_t)(L.V_pad + 4);         // vwin
-    w += 64 * 9;                        // per-player arrays
+    w += 64 * 10;                       // per-player arrays
     w += 256;                           // oobx, ooby
     w += (size_t)(L.F_pad + 4);         // freefood
-    w += 16;                            // scalars
+    w += 64;                            // scalars + alive-list membership bits
     return w * 4 + 16;
 }
 
@@ -173,18 +195,29 @@ __device__ __forceinline__ Smem carve(float* base, const AgarLayout& L, int G) {
     Smem s;
     float* p = base;
     s.rec = p; s.reci = (int32_t*)p; p += L.words;           // words % 4 == 0
-    s.tile = p; p += G * G;                                  // G % 4 == 0
-    s.list = (float4*)p; p += L.cells_total * 4;
+    s.tile = p;
+    {
+        int32_t* h = (int32_t*)p;
+        s.hstart = h; h += HASH_BINS + 1 + 3;
+        s.hcur = h; h += HASH_BINS;
+        s.pwin = h; h += L.P_pad;
+        s.sorted = (uint16_t*)h; h += L.P_pad / 2;
+        s.hits = (uint16_t*)h; h += L.P_pad / 2;
+        s.extras = (uint16_t*)h;
+    }
+    p += union_words(L, G);
+    s.list = (int32_t*)p; p += L.cells_total;
     s.cnt = (int32_t*)p; p += L.cells_total;
+    s.eater = (int32_t*)p; p += L.cells_total;
     s.gain = p; p += L.cells_total;
     s.first = (int32_t*)p; p += L.cells_total;
     s.vwin = (int32_t*)p; p += L.V_pad + 4;
     s.Tx = p; p += 64; s.Ty = p; p += 64; s.dirx = p; p += 64; s.diry = p; p += 64;
     s.Cx = p; p += 64; s.Cy = p; p += 64; s.mass0 = p; p += 64;
-    s.pact = (int32_t*)p; p += 64; s.palive = (int32_t*)p; p += 64;
+    s.pact = (int32_t*)p; p += 64; s.palive = (int32_t*)p; p += 64; s.pmask = (int32_t*)p; p += 64;
     s.oobx = (int32_t*)p; p += 128; s.ooby = (int32_t*)p; p += 128;
     s.freefood = (int32_t*)p; p += L.F_pad + 4;
-    s.sc = (int32_t*)p; p += 16;
+    s.sc = (int32_t*)p; p += 64;
     return s;
 }
 
@@ -235,23 +268,74 @@ __device__ void reset_arena(const DevParams& p, const Smem& s, uint32_t gid_lo, 
     __syncthreads();
 }
 
-// warp 0: ordered list of alive cells (x, y, r2, gid); ascending gid so "first hit" == lowest gid
+// pellet bin: monotone in the coordinate, so a conservative coordinate range maps to a bin range
+__device__ __forceinline__ int hash_coord(const DevParams& p, float v) {
+    int b = (int)(v * p.hash_inv);
+    return b < 0 ? 0 : (b > HASH_W - 1 ? HASH_W - 1 : b);
+}
+
+// counting sort of the present pellets into the HASH_W x HASH_W grid (all threads; ends synchronised).
+// Order inside a bin is arbitrary: every consumer reduces with min / integer counts.
+__device__ void build_hash(const DevParams& p, const Smem& s) {
+    const AgarLayout& L = p.L;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, P = p.c.num_pellets;
+    const float* px = s.rec + L.pellet_x; const float* py = s.rec + L.pellet_y;
+    for (int i = tid; i < HASH_BINS; i += nt) s.hcur[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < P; i += nt) {
+        float x = px[i];
+        s.pwin[i] = NONE_I;
+        if (x >= 0.0f) atomicAdd(&s.hcur[hash_coord(p, py[i]) * HASH_W + hash_coord(p, x)], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+        constexpr int PER = HASH_BINS / 32;
+        int c[PER], tot = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { c[q] = s.hcur[lane * PER + q]; tot += c[q]; }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int run = incl - tot;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { s.hstart[lane * PER + q] = run; s.hcur[lane * PER + q] = run; run += c[q]; }
+        if (lane == 31) s.hstart[HASH_BINS] = incl;
+        if (lane == 0) { s.sc[SC_NEXTRAS] = 0; s.sc[SC_REBUILD] = 0; s.sc[SC_NHITS] = 0; }
+    }
+    __syncthreads();
+    for (int i = tid; i < P; i += nt) {
+        float x = px[i];
+        if (x >= 0.0f) {
+            int pos = atomicAdd(&s.hcur[hash_coord(p, py[i]) * HASH_W + hash_coord(p, x)], 1);
+            s.sorted[pos] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+}
+
+// all threads: unordered list of the alive cells' gids, per-player alive masks, "some player has
+// several cells" flag.  SC_NLIST and SC_MULTI must be 0 on entry (a barrier earlier).
 __device__ __forceinline__ void build_list(const DevParams& p, const Smem& s) {
     const AgarLayout& L = p.L;
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        int n = 0;
-        for (int base = 0; base < p.KC; base += 32) {
-            int g = base + lane;
-            float m = (g < p.KC) ? s.rec[L.cell_m + g] : 0.0f;
-            bool al = m > 0.0f;
-            unsigned b = __ballot_sync(0xffffffffu, al);
-            if (al)
-                s.list[n + __popc(b & ((1u << lane) - 1u))] =
-                    make_float4(s.rec[L.cell_x + g], s.rec[L.cell_y + g], m * p.c.r2_per_mass, __int_as_float(g));
-            n += __popc(b);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    for (int base = 0; base < p.KC; base += nt) {
+        const int g = base + tid;
+        const bool al = g < p.KC && s.rec[L.cell_m + g] > 0.0f;
+        const unsigned b = __ballot_sync(0xffffffffu, al);
+        if (g < p.KC && (lane & 15) == 0) {
+            unsigned hm = (b >> (lane & 16)) & 0xFFFFu;
+            s.pmask[g >> 4] = (int)hm;
+            if (__popc(hm) >= 2) s.sc[SC_MULTI] = 1;
         }
-        if (lane == 0) s.sc[SC_NLIST] = n;
+        if (b) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(&s.sc[SC_NLIST], __popc(b));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (al) s.list[pos + __popc(b & ((1u << lane) - 1u))] = g;
+        }
     }
 }
 
@@ -266,6 +350,11 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
     const float box = p.box, arena = p.c.arena_size, view = p.c.view_size;
     const int half = G / 2;
 
+    // the tile shares its memory with the pellet hash: clear it first
+    {
+        float4* t4 = reinterpret_cast<float4*>(s.tile);
+        for (int i = tid; i < GG / 4; i += nt) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     // centroids of all agents (half-warp per agent)
     for (int g = tid; g < A * MC; g += nt) {
         int k = g >> 4;
@@ -362,10 +451,19 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
 }
 
 // --------------------------------------------------------------------------- the kernel
-// grid = number of arenas (records); block = AGAR_THREADS; dynamic smem = smem_bytes().
+// grid = number of arenas (records); block = kThreads; dynamic smem = smem_bytes().
+//
+// Phase plan of one step (B = __syncthreads):
+//   stage record | B | pellet hash (counting sort) | alive list + player masks | B | players:
+//   respawn, centroid, targets | B | bots pick targets through the hash, split, feed | B |
+//   per tick:  motion + pellet query (one thread per alive cell, hash neighbourhood + extras) | B |
+//              resolve claimed pellets (count, respawn by Philox, extras) | B |
+//              apply gains + virus claims | B | [pops] | cell-eats-cell test | B | [apply] |
+//              merge (half-warp per player, shuffles) | B
+//   rewards/dones | B | write back | raster.
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads) agar_step_kernel(const __grid_constant__ DevParams p,
-                                                            const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_constant__ DevParams p,
+                                                               const __grid_constant__ KArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
     const AgarLayout& L = p.L;
     const AgarConfig& c = p.c;
@@ -374,7 +472,7 @@ __global__ void __launch_bounds__(kThreads) agar_step_kernel(const __grid_consta
     const int hbase = lane & 16, slot = lane & 15;
     const unsigned hmask = 0xFFFFu << hbase;
     const int arena = blockIdx.x;
-    const int A = c.num_agents, K = p.K, KC = p.KC, P = c.num_pellets, V = c.num_viruses, F = c.max_foods;
+    const int A = c.num_agents, K = p.K, KC = p.KC, V = c.num_viruses, F = c.max_foods;
     const uint64_t gid64 = (uint64_t)(c.arena_id_base + arena);
     const uint32_t gid_lo = (uint32_t)gid64, gid_hi = (uint32_t)(gid64 >> 32);
     const float r2pm = c.r2_per_mass, arena_size = c.arena_size;
@@ -384,15 +482,15 @@ __global__ void __launch_bounds__(kThreads) agar_step_kernel(const __grid_consta
     float* vx = s.rec + L.virus_x; float* vy = s.rec + L.virus_y;
     float* fx = s.rec + L.food_x; float* fy = s.rec + L.food_y; float* fvx = s.rec + L.food_vx; float* fvy = s.rec + L.food_vy;
     float* grec = a.state + (size_t)arena * L.words;  // write target
+    int32_t* inl = s.sc + 16;                         // bitmask of gids present in the alive list
 
     // ---- stage the record ----
     {
         const float4* src = reinterpret_cast<const float4*>(a.src_state + (size_t)arena * L.words);
         float4* dst = reinterpret_cast<float4*>(s.rec);
         for (int i = tid; i < L.words / 4; i += nt) dst[i] = __ldg(src + i);
-        float4* t4 = reinterpret_cast<float4*>(s.tile);
-        for (int i = tid; i < c.grid_size * c.grid_size / 4; i += nt) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tid < 16) s.sc[tid] = 0;
+        for (int i = tid; i < KC; i += nt) { s.cnt[i] = 0; s.eater[i] = NONE_I; s.gain[i] = 0.0f; s.first[i] = NONE_I; }
+        if (tid < 64) s.sc[tid] = 0;
     }
     __syncthreads();
 
@@ -403,69 +501,93 @@ __global__ void __launch_bounds__(kThreads) agar_step_kernel(const __grid_consta
 
     if (a.flags & F_STEP) {
         const uint32_t tick0 = (uint32_t)s.reci[L.tick];
-        // ---- step start: mass before, bot respawn, centroids, targets ----
-        for (int g = tid; g < KC; g += nt) {
-            const int k = g >> 4;
-            float m = cm[g];
-            float mb = hw_treesum(hmask, m);
-            bool alive = __ballot_sync(hmask, m > 0.0f) != 0u;
-            if (k >= A && !alive) {  // dead bot: respawn (spawn_player in the oracle)
-                clear_cell(p, s, g);
-                if (slot == 0) {
-                    float x, y;
-                    rand_pos(p, gid_lo, gid_hi, (uint32_t)k, AGAR_STREAM_PLAYER_SPAWN, tick0, x, y);
-                    cx[g] = x; cy[g] = y; cm[g] = c.start_mass;
-                    ev_push(p, a, s, arena, 0, AGAR_EV_RESPAWN, k, 0);
-                }
-                __syncwarp(hmask);
-                m = cm[g];
-                alive = true;
-            }
-            float Cx = 0.0f, Cy = 0.0f;
-            if (alive) hw_centroid(hmask, hbase, slot, cx[g], cy[g], m, Cx, Cy);
-            if (slot == 0) {
-                s.palive[k] = alive ? 1 : 0;
-                s.Cx[k] = Cx; s.Cy[k] = Cy;
-                s.pact[k] = 0; s.Tx[k] = 0.0f; s.Ty[k] = 0.0f; s.dirx[k] = 1.0f; s.diry[k] = 0.0f;
-                if (k < A) {
-                    s.mass0[k] = mb;
-                    if (alive) {
-                        float ax, ay; int act;
-                        const size_t ia = (size_t)arena * A + k;
-                        if (a.act_index) {
-                            int idx = a.act_index[ia];
-                            idx = idx < 0 ? 0 : (idx >= a.n_actions ? a.n_actions - 1 : idx);
-                            ax = a.tab_xy[2 * idx]; ay = a.tab_xy[2 * idx + 1]; act = a.tab_act[idx];
-                        } else {
-                            ax = a.target_xy[2 * ia]; ay = a.target_xy[2 * ia + 1]; act = a.act[ia];
-                        }
-                        float n2 = ax * ax + ay * ay;
-                        if (!(n2 < INFINITY)) { ax = 0.0f; ay = 0.0f; }
-                        else if (n2 > 1.0f) { float inv = 1.0f / sqrtf(n2); ax = ax * inv; ay = ay * inv; }
-                        s.Tx[k] = Cx + ax * c.target_reach;
-                        s.Ty[k] = Cy + ay * c.target_reach;
-                        float m2 = ax * ax + ay * ay;
-                        if (m2 > 0.0f) { float inv = 1.0f / sqrtf(m2); s.dirx[k] = ax * inv; s.diry[k] = ay * inv; }
-                        act = (act == AGAR_ACT_SPLIT || act == AGAR_ACT_FEED) ? act : 0;
-                        s.pact[k] = act;
-                        if (act == AGAR_ACT_FEED) s.sc[SC_ANYFEED] = 1;
-                        if (act == AGAR_ACT_SPLIT) s.sc[SC_ANYSPLIT] = 1;
-                    }
-                }
-            }
+        // ---- pellet hash, alive list ----
+        build_hash(p, s);
+        build_list(p, s);
+        for (int base = 0; base < KC; base += nt) {  // membership bits of the list (one word per warp chunk)
+            const int g = base + tid;
+            const unsigned b = __ballot_sync(0xffffffffu, g < KC && cm[g] > 0.0f);
+            if (lane == 0 && g < KC) inl[g >> 5] = (int)b;
         }
         __syncthreads();
-        // ---- bots: nearest pellet in the square sense window, else roam way-point (warp per bot) ----
+        // ---- players: bot respawn, centroid and mass of single-cell players (thread per player) ----
+        for (int k = tid; k < K; k += nt) {
+            unsigned pm = (unsigned)s.pmask[k];
+            if (k >= A && pm == 0u) {  // dead bot: respawn (spawn_player in the oracle)
+                const int g = k * MC;
+                float x, y;
+                rand_pos(p, gid_lo, gid_hi, (uint32_t)k, AGAR_STREAM_PLAYER_SPAWN, tick0, x, y);
+                cx[g] = x; cy[g] = y; cm[g] = c.start_mass;  // the other fields of a dead player's slots are 0
+                ev_push(p, a, s, arena, 0, AGAR_EV_RESPAWN, k, 0);
+                pm = 1u; s.pmask[k] = 1;
+                if (!(atomicOr(&inl[g >> 5], 1 << (g & 31)) & (1 << (g & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = g;
+            }
+            s.palive[k] = pm != 0u;
+            s.pact[k] = 0; s.Tx[k] = 0.0f; s.Ty[k] = 0.0f; s.dirx[k] = 1.0f; s.diry[k] = 0.0f;
+            float Cx = 0.0f, Cy = 0.0f, mb = 0.0f;
+            if (__popc(pm) == 1) {  // np.average over one cell: (x*m)/m, exactly as the general path gives
+                const int g = k * MC + __ffs(pm) - 1;
+                const float m = cm[g];
+                Cx = (cx[g] * m) / m; Cy = (cy[g] * m) / m; mb = m;
+            }
+            s.Cx[k] = Cx; s.Cy[k] = Cy;
+            if (k < A) s.mass0[k] = mb;
+        }
+        __syncthreads();
+        // ---- players with several cells: numpy-order centroid and butterfly mass (half-warp per player) ----
+        if (s.sc[SC_MULTI]) {
+            for (int g = tid; g < KC; g += nt) {
+                const int k = g >> 4;
+                if (__popc((unsigned)s.pmask[k]) < 2) continue;  // uniform per half-warp
+                const float m = cm[g];
+                float Cx = 0.0f, Cy = 0.0f;
+                hw_centroid(hmask, hbase, slot, cx[g], cy[g], m, Cx, Cy);
+                const float mb = hw_treesum(hmask, m);
+                if (slot == 0) { s.Cx[k] = Cx; s.Cy[k] = Cy; if (k < A) s.mass0[k] = mb; }
+            }
+            __syncthreads();
+        }
+        // ---- agents: action -> target point, direction, act ----
+        for (int k = tid; k < A; k += nt) {
+            if (!s.palive[k]) continue;
+            float ax, ay; int act;
+            const size_t ia = (size_t)arena * A + k;
+            if (a.act_index) {
+                int idx = a.act_index[ia];
+                idx = idx < 0 ? 0 : (idx >= a.n_actions ? a.n_actions - 1 : idx);
+                ax = a.tab_xy[2 * idx]; ay = a.tab_xy[2 * idx + 1]; act = a.tab_act[idx];
+            } else {
+                ax = a.target_xy[2 * ia]; ay = a.target_xy[2 * ia + 1]; act = a.act[ia];
+            }
+            float n2 = ax * ax + ay * ay;
+            if (!(n2 < INFINITY)) { ax = 0.0f; ay = 0.0f; }
+            else if (n2 > 1.0f) { float inv = 1.0f / sqrtf(n2); ax = ax * inv; ay = ay * inv; }
+            s.Tx[k] = s.Cx[k] + ax * c.target_reach;
+            s.Ty[k] = s.Cy[k] + ay * c.target_reach;
+            float m2 = ax * ax + ay * ay;
+            if (m2 > 0.0f) { float inv = 1.0f / sqrtf(m2); s.dirx[k] = ax * inv; s.diry[k] = ay * inv; }
+            act = (act == AGAR_ACT_SPLIT || act == AGAR_ACT_FEED) ? act : 0;
+            s.pact[k] = act;
+            if (act == AGAR_ACT_FEED) s.sc[SC_ANYFEED] = 1;
+            if (act == AGAR_ACT_SPLIT) s.sc[SC_ANYSPLIT] = 1;
+        }
+        // ---- bots: nearest pellet in the square sense window (hash neighbourhood, warp per bot),
+        //      else the roam way-point ----
         for (int k = A + (tid >> 5); k < K; k += nt >> 5) {
             const float Cx = s.Cx[k], Cy = s.Cy[k], R = c.bot_sense_radius;
+            const float Rp = R * 1.001f + 0.01f;
+            const int bx0 = hash_coord(p, Cx - Rp), bx1 = hash_coord(p, Cx + Rp);
+            const int by0 = hash_coord(p, Cy - Rp), by1 = hash_coord(p, Cy + Rp);
             float best = INFINITY; int bi = NONE_I;
-            for (int i = lane; i < P; i += 32) {
-                float x = px[i];
-                if (!(x >= 0.0f)) continue;
-                float dx = x - Cx, dy = py[i] - Cy;
-                if (fabsf(dx) <= R && fabsf(dy) <= R) {
-                    float d2 = dx * dx + dy * dy;
-                    if (d2 < best) { best = d2; bi = i; }
+            for (int by = by0; by <= by1; ++by) {
+                const int j1 = s.hstart[by * HASH_W + bx1 + 1];
+                for (int j = s.hstart[by * HASH_W + bx0] + lane; j < j1; j += 32) {
+                    const int i = s.sorted[j];
+                    float dx = px[i] - Cx, dy = py[i] - Cy;
+                    if (fabsf(dx) <= R && fabsf(dy) <= R) {
+                        float d2 = dx * dx + dy * dy;
+                        if (d2 < best || (d2 == best && i < bi)) { best = d2; bi = i; }
+                    }
                 }
             }
 #pragma unroll
@@ -484,6 +606,7 @@ __global__ void __launch_bounds__(kThreads) agar_step_kernel(const __grid_consta
                 }
             }
         }
+        __syncthreads();
         // ---- split: i-th eligible cell -> i-th free slot (ballot ranks inside the half-warp) ----
         if (s.sc[SC_ANYSPLIT]) {
             for (int g = tid; g < A * MC; g += nt) {
@@ -502,6 +625,8 @@ __global__ void __launch_bounds__(kThreads) agar_step_kernel(const __grid_consta
                     cix[d] = s.dirx[k] * c.split_speed; ciy[d] = s.diry[k] * c.split_speed;
                     cm[d] = halfm; ct[d] = c.merge_delay;
                     ev_push(p, a, s, arena, 0, AGAR_EV_SPLIT, g, d);
+                    s.sc[SC_MULTI] = 1;
+                    if (!(atomicOr(&inl[d >> 5], 1 << (d & 31)) & (1 << (d & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = d;
                 }
             }
         }
@@ -541,179 +666,206 @@ __global__ void __launch_bounds__(kThreads) agar_step_kernel(const __grid_consta
 
         for (int tk = 0; tk < c.ticks_per_step; ++tk) {
             const uint32_t tick = tick0 + (uint32_t)tk;
-            // ---- motion ----
-            for (int g = tid; g < KC; g += nt) {
-                float m = cm[g];
-                s.cnt[g] = 0;
-                if (!(m > 0.0f)) continue;
-                const int k = g >> 4;
-                float r = sqrtf(m * r2pm);
-                float spd = c.speed_k / sqrtf(r);
-                float dx = s.Tx[k] - cx[g], dy = s.Ty[k] - cy[g];
-                float d = sqrtf(dx * dx + dy * dy);
-                float den = d > c.target_reach ? d : c.target_reach;
-                float sc = spd / den;
-                float nx = cx[g] + (dx * sc + cix[g]);
-                float ny = cy[g] + (dy * sc + ciy[g]);
-                float ix = cix[g] * c.impulse_decay, iy = ciy[g] * c.impulse_decay;
-                if (fabsf(ix) < 1e-3f && fabsf(iy) < 1e-3f) { ix = 0.0f; iy = 0.0f; }
-                cx[g] = clampf(nx, 0.0f, arena_size); cy[g] = clampf(ny, 0.0f, arena_size);
-                cix[g] = ix; ciy[g] = iy;
-                float t = ct[g];
-                if (t > 0.0f) ct[g] = t - 1.0f;
-            }
-            for (int f = tid; f < F; f += nt)
-                if (fx[f] >= 0.0f) s.sc[SC_FOODANY] = 1;
-            for (int v = tid; v < V; v += nt) s.vwin[v] = NONE_I;
-            __syncthreads();
-            build_list(p, s);
-            __syncthreads();
-            // ---- pellets: each pellet looks for the lowest-gid cell whose disc holds its centre ----
+            if (s.sc[SC_REBUILD]) build_hash(p, s);  // too many respawns since the last build (uniform)
+            // ---- motion + pellet query: one thread per alive cell ----
             {
                 const int n = s.sc[SC_NLIST];
-                for (int i = tid; i < P; i += nt) {
-                    float x = px[i];
-                    if (!(x >= 0.0f)) continue;
-                    float y = py[i];
-                    for (int j = 0; j < n; ++j) {
-                        float4 cl = s.list[j];
-                        float dx = x - cl.x, dy = y - cl.y;
-                        if (dx * dx + dy * dy < cl.z) {
-                            int g = __float_as_int(cl.w);
-                            atomicAdd(&s.cnt[g], 1);
-                            ev_push(p, a, s, arena, tk, AGAR_EV_PELLET_EATEN, g, i);
-                            float nx = -1.0f, ny = -1.0f;
-                            if (c.pellet_regen) rand_pos(p, gid_lo, gid_hi, (uint32_t)i, AGAR_STREAM_PELLET_RESPAWN, tick, nx, ny);
-                            px[i] = nx; py[i] = ny;
-                            if (!(a.flags & F_READONLY)) { grec[L.pellet_x + i] = nx; grec[L.pellet_y + i] = ny; }
-                            break;
+                const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
+                for (int q = tid; q < n; q += nt) {
+                    const int g = s.list[q];
+                    const float m = cm[g];
+                    if (!(m > 0.0f)) continue;  // died earlier in this step
+                    const int k = g >> 4;
+                    const float r2 = m * r2pm;
+                    const float r = sqrtf(r2);
+                    float spd = c.speed_k / sqrtf(r);
+                    float dx = s.Tx[k] - cx[g], dy = s.Ty[k] - cy[g];
+                    float d = sqrtf(dx * dx + dy * dy);
+                    float den = d > c.target_reach ? d : c.target_reach;
+                    float sc = spd / den;
+                    float nx = cx[g] + (dx * sc + cix[g]);
+                    float ny = cy[g] + (dy * sc + ciy[g]);
+                    float ix = cix[g] * c.impulse_decay, iy = ciy[g] * c.impulse_decay;
+                    if (fabsf(ix) < 1e-3f && fabsf(iy) < 1e-3f) { ix = 0.0f; iy = 0.0f; }
+                    const float x = clampf(nx, 0.0f, arena_size), y = clampf(ny, 0.0f, arena_size);
+                    cx[g] = x; cy[g] = y; cix[g] = ix; ciy[g] = iy;
+                    float t = ct[g];
+                    if (t > 0.0f) ct[g] = t - 1.0f;
+                    // pellets whose centre lies inside the disc: bins overlapped by the (padded) bounding box
+                    const float rp = r * 1.001f + 0.01f;
+                    const int bx0 = hash_coord(p, x - rp), bx1 = hash_coord(p, x + rp);
+                    const int by0 = hash_coord(p, y - rp), by1 = hash_coord(p, y + rp);
+                    for (int by = by0; by <= by1; ++by) {
+                        const int j1 = s.hstart[by * HASH_W + bx1 + 1];
+                        for (int j = s.hstart[by * HASH_W + bx0]; j < j1; ++j) {
+                            const int i = s.sorted[j];
+                            const float qx = px[i];
+                            if (!(qx >= 0.0f)) continue;
+                            const float ex = qx - x, ey = py[i] - y;
+                            if (ex * ex + ey * ey < r2)
+                                if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
                         }
                     }
+                    for (int e = 0; e < nex; ++e) {  // respawned since the hash was built
+                        const int i = s.extras[e];
+                        const float ex = px[i] - x, ey = py[i] - y;
+                        if (ex * ex + ey * ey < r2)
+                            if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
+                    }
+                }
+                for (int f = tid; f < F; f += nt)
+                    if (fx[f] >= 0.0f) s.sc[SC_FOODANY] = 1;
+                for (int v = tid; v < V; v += nt) s.vwin[v] = NONE_I;
+            }
+            __syncthreads();
+            // ---- resolve the claimed pellets: winner = lowest gid (atomicMin), respawn by Philox ----
+            {
+                const int nh = s.sc[SC_NHITS];
+                for (int h = tid; h < nh; h += nt) {
+                    const int i = s.hits[h];
+                    const int g = s.pwin[i];
+                    s.pwin[i] = NONE_I;
+                    atomicAdd(&s.cnt[g], 1);
+                    ev_push(p, a, s, arena, tk, AGAR_EV_PELLET_EATEN, g, i);
+                    float nx = -1.0f, ny = -1.0f;
+                    if (c.pellet_regen) {
+                        rand_pos(p, gid_lo, gid_hi, (uint32_t)i, AGAR_STREAM_PELLET_RESPAWN, tick, nx, ny);
+                        const int e = atomicAdd(&s.sc[SC_NEXTRAS], 1);
+                        if (e < EXTRA_CAP) s.extras[e] = (uint16_t)i; else s.sc[SC_REBUILD] = 1;
+                    }
+                    px[i] = nx; py[i] = ny;
+                    if (!(a.flags & F_READONLY)) { grec[L.pellet_x + i] = nx; grec[L.pellet_y + i] = ny; }
                 }
             }
             __syncthreads();
-            for (int g = tid; g < KC; g += nt) {
-                int n = s.cnt[g];
-                if (n) { cm[g] = cm[g] + (float)n * c.pellet_mass; s.cnt[g] = 0; }
-            }
-            // ---- foods: move, then eaten like pellets ----
-            if (s.sc[SC_FOODANY]) {  // block-uniform (written before the last barrier)
-                __syncthreads();
-                build_list(p, s);
-                __syncthreads();
+            const bool food_any = s.sc[SC_FOODANY] != 0;  // block-uniform
+            if (food_any) {
+                // ---- pellet gains, then foods: move, eaten by the lowest-gid cell holding the centre ----
                 const int n = s.sc[SC_NLIST];
+                for (int q = tid; q < n; q += nt) {
+                    const int g = s.list[q];
+                    const int e = s.cnt[g];
+                    if (e) { cm[g] = cm[g] + (float)e * c.pellet_mass; s.cnt[g] = 0; }
+                }
+                __syncthreads();
                 for (int f = tid; f < F; f += nt) {
                     float x = fx[f];
                     if (!(x >= 0.0f)) continue;
                     float nx = x + fvx[f], ny = fy[f] + fvy[f];
                     float ux = fvx[f] * c.food_decay, uy = fvy[f] * c.food_decay;
                     if (fabsf(ux) < 1e-3f && fabsf(uy) < 1e-3f) { ux = 0.0f; uy = 0.0f; }
-                    x = clampf(nx, 0.0f, arena_size); float y = clampf(ny, 0.0f, arena_size);
+                    x = clampf(nx, 0.0f, arena_size); const float y = clampf(ny, 0.0f, arena_size);
                     fx[f] = x; fy[f] = y; fvx[f] = ux; fvy[f] = uy;
-                    for (int j = 0; j < n; ++j) {
-                        float4 cl = s.list[j];
-                        float dx = x - cl.x, dy = y - cl.y;
-                        if (dx * dx + dy * dy < cl.z) {
-                            int g = __float_as_int(cl.w);
-                            atomicAdd(&s.cnt[g], 1);
-                            ev_push(p, a, s, arena, tk, AGAR_EV_FOOD_EATEN, g, f);
-                            fx[f] = -1.0f; fy[f] = 0.0f; fvx[f] = 0.0f; fvy[f] = 0.0f;
-                            break;
-                        }
+                    int best = NONE_I;
+                    for (int q = 0; q < n; ++q) {
+                        const int g = s.list[q];
+                        const float m = cm[g];
+                        const float dx = x - cx[g], dy = y - cy[g];
+                        if (m > 0.0f && dx * dx + dy * dy < m * r2pm && g < best) best = g;
+                    }
+                    if (best != NONE_I) {
+                        atomicAdd(&s.cnt[best], 1);
+                        ev_push(p, a, s, arena, tk, AGAR_EV_FOOD_EATEN, best, f);
+                        fx[f] = -1.0f; fy[f] = 0.0f; fvx[f] = 0.0f; fvy[f] = 0.0f;
                     }
                 }
                 __syncthreads();
-                for (int g = tid; g < KC; g += nt) {
-                    int n2 = s.cnt[g];
-                    if (n2) { cm[g] = cm[g] + (float)n2 * c.food_mass; s.cnt[g] = 0; }
+            }
+            // ---- apply gains (pellets, or foods when present); heavy cells claim viruses ----
+            {
+                const int n = s.sc[SC_NLIST];
+                const float unit = food_any ? c.food_mass : c.pellet_mass;
+                for (int q = tid; q < n; q += nt) {
+                    const int g = s.list[q];
+                    float m = cm[g];
+                    const int e = s.cnt[g];
+                    if (e) { m = m + (float)e * unit; cm[g] = m; s.cnt[g] = 0; }
+                    if (V > 0 && m >= c.virus_pop_mass) {
+                        const float r2 = m * r2pm, x = cx[g], y = cy[g];
+                        for (int v = 0; v < V; ++v) {
+                            float dx = vx[v] - x, dy = vy[v] - y;
+                            if (dx * dx + dy * dy < r2) { atomicMin(&s.vwin[v], g); s.sc[SC_ANYVHIT] = 1; }
+                        }
+                    }
                 }
-                if (tid == 0) s.sc[SC_FOODANY] = 0;
+                if (tid == 0) { s.sc[SC_NHITS] = 0; s.sc[SC_FOODANY] = 0; }
             }
             __syncthreads();
-            // ---- viruses: heavy cells claim the viruses inside them (atomicMin = lowest gid) ----
-            if (V > 0) {
-                for (int g = tid; g < KC; g += nt) {
-                    float m = cm[g];
-                    s.first[g] = NONE_I;
-                    if (!(m >= c.virus_pop_mass)) continue;
-                    float r2 = m * r2pm, x = cx[g], y = cy[g];
-                    for (int v = 0; v < V; ++v) {
-                        float dx = vx[v] - x, dy = vy[v] - y;
-                        if (dx * dx + dy * dy < r2) { atomicMin(&s.vwin[v], g); s.sc[SC_ANYVHIT] = 1; }
+            // ---- virus pops ----
+            if (s.sc[SC_ANYVHIT]) {  // block-uniform, rare
+                const int n = s.sc[SC_NLIST];
+                for (int q = tid; q < n; q += nt) {
+                    const int g = s.list[q];
+                    if (!(cm[g] >= c.virus_pop_mass)) continue;
+                    for (int v = 0; v < V; ++v)
+                        if (s.vwin[v] == g) { s.first[g] = v; break; }
+                }
+                __syncthreads();
+                // one thread per player walks its slots in order (free slots are consumed sequentially
+                // inside a player, exactly as the oracle does)
+                for (int k = tid; k < K; k += nt) {
+                    for (int sl = 0; sl < MC; ++sl) {
+                        const int g = k * MC + sl;
+                        const int v = s.first[g];
+                        if (v == NONE_I) continue;
+                        s.first[g] = NONE_I;
+                        float m1 = cm[g] + c.virus_mass;
+                        int freeslot[MC]; int nfree = 0;
+                        for (int q = 0; q < MC; ++q)
+                            if (cm[k * MC + q] == 0.0f) freeslot[nfree++] = q;
+                        int np = nfree < c.pop_pieces ? nfree : c.pop_pieces;
+                        ev_push(p, a, s, arena, tk, AGAR_EV_VIRUS_POP, g, v);
+                        if (np > 0) {
+                            const float DX[16] = AGAR_DIR16_X; const float DY[16] = AGAR_DIR16_Y;
+                            float keep = m1 * 0.5f;
+                            float piece = (m1 - keep) / (float)np;
+                            cm[g] = keep; ct[g] = c.merge_delay;
+                            for (int j = 0; j < np; ++j) {
+                                int d = k * MC + freeslot[j];
+                                cx[d] = cx[g]; cy[d] = cy[g];
+                                cix[d] = DX[j] * c.pop_speed; ciy[d] = DY[j] * c.pop_speed;
+                                cm[d] = piece; ct[d] = c.merge_delay;
+                                ev_push(p, a, s, arena, tk, AGAR_EV_POP_PIECE, g, d);
+                                if (!(atomicOr(&inl[d >> 5], 1 << (d & 31)) & (1 << (d & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = d;
+                            }
+                            s.sc[SC_MULTI] = 1;
+                        } else {
+                            cm[g] = m1;
+                        }
+                        float nx, ny;
+                        rand_pos(p, gid_lo, gid_hi, (uint32_t)v, AGAR_STREAM_VIRUS_RESPAWN, tick, nx, ny);
+                        vx[v] = nx; vy[v] = ny;
+                        if (!(a.flags & F_READONLY)) { grec[L.virus_x + v] = nx; grec[L.virus_y + v] = ny; }
                     }
                 }
                 __syncthreads();
-                if (s.sc[SC_ANYVHIT]) {
-                    for (int g = tid; g < KC; g += nt) {
-                        if (!(cm[g] >= c.virus_pop_mass)) continue;
-                        for (int v = 0; v < V; ++v)
-                            if (s.vwin[v] == g) { s.first[g] = v; break; }
-                    }
-                    __syncthreads();
-                    // pops: one thread per player walks its slots in order (free slots are consumed
-                    // sequentially inside a player, exactly as the oracle does)
-                    for (int k = tid; k < K; k += nt) {
-                        for (int sl = 0; sl < MC; ++sl) {
-                            const int g = k * MC + sl;
-                            const int v = s.first[g];
-                            if (v == NONE_I) continue;
-                            float m1 = cm[g] + c.virus_mass;
-                            int freeslot[MC]; int nfree = 0;
-                            for (int q = 0; q < MC; ++q)
-                                if (cm[k * MC + q] == 0.0f) freeslot[nfree++] = q;
-                            int np = nfree < c.pop_pieces ? nfree : c.pop_pieces;
-                            ev_push(p, a, s, arena, tk, AGAR_EV_VIRUS_POP, g, v);
-                            if (np > 0) {
-                                const float DX[16] = AGAR_DIR16_X; const float DY[16] = AGAR_DIR16_Y;
-                                float keep = m1 * 0.5f;
-                                float piece = (m1 - keep) / (float)np;
-                                cm[g] = keep; ct[g] = c.merge_delay;
-                                for (int j = 0; j < np; ++j) {
-                                    int d = k * MC + freeslot[j];
-                                    cx[d] = cx[g]; cy[d] = cy[g];
-                                    cix[d] = DX[j] * c.pop_speed; ciy[d] = DY[j] * c.pop_speed;
-                                    cm[d] = piece; ct[d] = c.merge_delay;
-                                    ev_push(p, a, s, arena, tk, AGAR_EV_POP_PIECE, g, d);
-                                }
-                            } else {
-                                cm[g] = m1;
-                            }
-                            float nx, ny;
-                            rand_pos(p, gid_lo, gid_hi, (uint32_t)v, AGAR_STREAM_VIRUS_RESPAWN, tick, nx, ny);
-                            vx[v] = nx; vy[v] = ny;
-                            if (!(a.flags & F_READONLY)) { grec[L.virus_x + v] = nx; grec[L.virus_y + v] = ny; }
-                        }
-                    }
-                    __syncthreads();
-                    if (tid == 0) s.sc[SC_ANYVHIT] = 0;
-                }
+                if (tid == 0) s.sc[SC_ANYVHIT] = 0;
             }
             // ---- cell eats cell (different players) on the pre-phase snapshot ----
             if (K > 1) {
-                __syncthreads();
-                build_list(p, s);
-                for (int g = tid; g < KC; g += nt) { s.cnt[g] = NONE_I; s.gain[g] = 0.0f; }
-                __syncthreads();
                 const int n = s.sc[SC_NLIST];
-                for (int j = tid; j < KC; j += nt) {
-                    float mj = cm[j];
+                for (int q = tid; q < n; q += nt) {
+                    const int j = s.list[q];
+                    const float mj = cm[j];
                     if (!(mj > 0.0f)) continue;
                     const float need = mj * c.eat_ratio, x = cx[j], y = cy[j];
                     const int kj = j >> 4;
-                    for (int q = 0; q < n; ++q) {
-                        float4 cl = s.list[q];
-                        int i = __float_as_int(cl.w);
-                        if ((i >> 4) == kj) continue;
-                        float dx = x - cl.x, dy = y - cl.y;
-                        if (dx * dx + dy * dy < cl.z && cm[i] >= need) { s.cnt[j] = i; s.sc[SC_ANYEAT] = 1; break; }
+                    int best = NONE_I;
+                    for (int qi = 0; qi < n; ++qi) {
+                        const int i = s.list[qi];
+                        const float mi = cm[i];
+                        if ((i >> 4) == kj || !(mi >= need)) continue;  // need > 0, so dead cells fail here
+                        const float dx = x - cx[i], dy = y - cy[i];
+                        if (dx * dx + dy * dy < mi * r2pm && i < best) best = i;
                     }
+                    if (best != NONE_I) { s.eater[j] = best; s.sc[SC_ANYEAT] = 1; }
                 }
                 __syncthreads();
                 if (s.sc[SC_ANYEAT]) {
                     if (tid < 32) {  // gains added in ascending prey order (float sum order is part of the spec)
                         for (int base = 0; base < KC; base += 32) {
                             int j = base + lane;
-                            int w = (j < KC) ? s.cnt[j] : NONE_I;
+                            int w = (j < KC) ? s.eater[j] : NONE_I;
                             unsigned mask = __ballot_sync(0xffffffffu, w != NONE_I);
                             while (mask) {
                                 int src = __ffs(mask) - 1;
@@ -727,47 +879,51 @@ __global__ void __launch_bounds__(kThreads) agar_step_kernel(const __grid_consta
                         }
                     }
                     __syncthreads();
-                    for (int g = tid; g < KC; g += nt) {
-                        if (s.cnt[g] != NONE_I) clear_cell(p, s, g);
+                    for (int q = tid; q < n; q += nt) {
+                        const int g = s.list[q];
+                        if (s.eater[g] != NONE_I) { clear_cell(p, s, g); s.eater[g] = NONE_I; }  // eaten: forfeits its gains
                         else if (s.gain[g] > 0.0f) cm[g] = cm[g] + s.gain[g];
+                        s.gain[g] = 0.0f;
                     }
                     if (tid == 0) s.sc[SC_ANYEAT] = 0;
+                    __syncthreads();
                 }
-                __syncthreads();
             }
             // ---- merge own cells whose timers ran out (half-warp per player, shuffles) ----
-            for (int g = tid; g < KC; g += nt) {
-                const float m = cm[g], t = ct[g], x = cx[g], y = cy[g];
-                const bool can = m > 0.0f && t == 0.0f;
-                unsigned canb = (__ballot_sync(hmask, can) >> hbase) & 0xFFFFu;
-                if (__popc(canb) < 2) continue;  // uniform per half-warp
-                const float r2 = m * r2pm;
-                int root = slot;
-                for (int q = 0; q < MC - 1; ++q) {
-                    float xa = __shfl_sync(hmask, x, hbase + q), ya = __shfl_sync(hmask, y, hbase + q);
-                    float ra = __shfl_sync(hmask, r2, hbase + q);
-                    if (can && root == slot && q < slot && ((canb >> q) & 1u)) {
-                        float dx = x - xa, dy = y - ya;
-                        float rr = ra > r2 ? ra : r2;
-                        if (dx * dx + dy * dy < rr) root = q;  // partner = lowest qualifying slot below
+            if (s.sc[SC_MULTI]) {
+                for (int g = tid; g < KC; g += nt) {
+                    const float m = cm[g], t = ct[g], x = cx[g], y = cy[g];
+                    const bool can = m > 0.0f && t == 0.0f;
+                    unsigned canb = (__ballot_sync(hmask, can) >> hbase) & 0xFFFFu;
+                    if (__popc(canb) < 2) continue;  // uniform per half-warp
+                    const float r2 = m * r2pm;
+                    int root = slot;
+                    for (int q = 0; q < MC - 1; ++q) {
+                        float xa = __shfl_sync(hmask, x, hbase + q), ya = __shfl_sync(hmask, y, hbase + q);
+                        float ra = __shfl_sync(hmask, r2, hbase + q);
+                        if (can && root == slot && q < slot && ((canb >> q) & 1u)) {
+                            float dx = x - xa, dy = y - ya;
+                            float rr = ra > r2 ? ra : r2;
+                            if (dx * dx + dy * dy < rr) root = q;  // partner = lowest qualifying slot below
+                        }
                     }
-                }
-                // follow partners down to the final survivor (partner < slot, so 4 jumps suffice)
+                    // follow partners down to the final survivor (partner < slot, so 4 jumps suffice)
 #pragma unroll
-                for (int it = 0; it < 4; ++it) root = __shfl_sync(hmask, root, hbase + root);
-                unsigned merged = (__ballot_sync(hmask, root != slot) >> hbase) & 0xFFFFu;
-                if (merged == 0u) continue;
-                float acc = m;
-                for (int q = 1; q < MC; ++q) {
-                    float mq = __shfl_sync(hmask, m, hbase + q);
-                    int rq = __shfl_sync(hmask, root, hbase + q);
-                    if (rq == slot && q != slot) acc = acc + mq;
-                }
-                if (root != slot) {
-                    ev_push(p, a, s, arena, tk, AGAR_EV_MERGE, (g & ~15) + root, g);
-                    clear_cell(p, s, g);
-                } else if (acc != m) {
-                    cm[g] = acc;
+                    for (int it = 0; it < 4; ++it) root = __shfl_sync(hmask, root, hbase + root);
+                    unsigned merged = (__ballot_sync(hmask, root != slot) >> hbase) & 0xFFFFu;
+                    if (merged == 0u) continue;
+                    float acc = m;
+                    for (int q = 1; q < MC; ++q) {
+                        float mq = __shfl_sync(hmask, m, hbase + q);
+                        int rq = __shfl_sync(hmask, root, hbase + q);
+                        if (rq == slot && q != slot) acc = acc + mq;
+                    }
+                    if (root != slot) {
+                        ev_push(p, a, s, arena, tk, AGAR_EV_MERGE, (g & ~15) + root, g);
+                        clear_cell(p, s, g);
+                    } else if (acc != m) {
+                        cm[g] = acc;
+                    }
                 }
             }
             __syncthreads();
@@ -810,6 +966,7 @@ __global__ void __launch_bounds__(kThreads) agar_step_kernel(const __grid_consta
     }
     // ---- observations ----
     if ((a.flags & F_OBS) && a.obs) {
+        __syncthreads();  // the tile shares memory with the pellet hash
         const int GG = c.grid_size * c.grid_size;
         raster_arena(p, s, a.obs + (size_t)arena * A * p.C * GG);
     }

@@ -252,6 +252,14 @@ static void ev_push(OracleEnv* e, int n, int tick, int type, int a, int b) {
     }
 }
 
+/* indices of the alive cells in ascending gid order (so "first hit" is the lowest gid) */
+static int alive_list(const float* cm, int KC, int* out) {
+    int n = 0;
+    for (int g = 0; g < KC; ++g)
+        if (cm[g] > 0.0f) out[n++] = g;
+    return n;
+}
+
 static void clear_cell(float* S, const AgarLayout* L, int g) {
     S[L->cell_x + g] = 0; S[L->cell_y + g] = 0; S[L->cell_ix + g] = 0;
     S[L->cell_iy + g] = 0; S[L->cell_m + g] = 0; S[L->cell_t + g] = 0;
@@ -392,7 +400,8 @@ static void step_arena(OracleEnv* e, int n, const float* target_xy, const int32_
         }
     }
 
-    int* win = (int*)malloc(sizeof(int) * (size_t)(KC + V + 8));
+    int* win = (int*)malloc(sizeof(int) * (size_t)(2 * KC + V + 8));
+    int* alive = win + KC + V + 8; int na;
     float* snap_m = (float*)malloc(sizeof(float) * (size_t)KC * 2);
     float* gain = snap_m + KC;
 
@@ -419,10 +428,11 @@ static void step_arena(OracleEnv* e, int n, const float* target_xy, const int32_
         }
         /* ---- pellets: eaten by the lowest-gid cell whose disc holds the pellet centre ---- */
         for (int g = 0; g < KC; ++g) { snap_m[g] = cm[g]; win[g] = 0; }
+        na = alive_list(cm, KC, alive);
         for (int p = 0; p < P; ++p) {
             if (!(px[p] >= 0.0f)) continue;
-            for (int g = 0; g < KC; ++g) {
-                if (!(snap_m[g] > 0.0f)) continue;
+            for (int q = 0; q < na; ++q) {
+                int g = alive[q];
                 float dx = px[p] - cx[g], dy = py[p] - cy[g];
                 if (dx * dx + dy * dy < snap_m[g] * r2pm) {
                     win[g]++;
@@ -437,6 +447,7 @@ static void step_arena(OracleEnv* e, int n, const float* target_xy, const int32_
             if (win[g]) cm[g] = cm[g] + (float)win[g] * c->pellet_mass;
         /* ---- foods: move, then eaten like pellets ---- */
         for (int g = 0; g < KC; ++g) { snap_m[g] = cm[g]; win[g] = 0; }
+        na = alive_list(cm, KC, alive);
         for (int f = 0; f < F; ++f) {
             if (!(fx[f] >= 0.0f)) continue;
             float nx = fx[f] + fvx[f], ny = fy[f] + fvy[f];
@@ -444,8 +455,8 @@ static void step_arena(OracleEnv* e, int n, const float* target_xy, const int32_
             if (fabsf(ux) < 1e-3f && fabsf(uy) < 1e-3f) { ux = 0.0f; uy = 0.0f; }
             fx[f] = clampf(nx, 0.0f, arena); fy[f] = clampf(ny, 0.0f, arena);
             fvx[f] = ux; fvy[f] = uy;
-            for (int g = 0; g < KC; ++g) {
-                if (!(snap_m[g] > 0.0f)) continue;
+            for (int q = 0; q < na; ++q) {
+                int g = alive[q];
                 float dx = fx[f] - cx[g], dy = fy[f] - cy[g];
                 if (dx * dx + dy * dy < snap_m[g] * r2pm) {
                     win[g]++;
@@ -461,10 +472,13 @@ static void step_arena(OracleEnv* e, int n, const float* target_xy, const int32_
         if (V > 0) {
             int* vwin = win + KC; /* [V] winner cell of each virus */
             for (int g = 0; g < KC; ++g) win[g] = NONE; /* first virus won by each cell */
+            na = 0;
+            for (int g = 0; g < KC; ++g)
+                if (cm[g] >= c->virus_pop_mass) alive[na++] = g; /* heavy enough to pop */
             for (int v = 0; v < V; ++v) {
                 vwin[v] = NONE;
-                for (int g = 0; g < KC; ++g) {
-                    if (!(cm[g] >= c->virus_pop_mass)) continue;
+                for (int q = 0; q < na; ++q) {
+                    int g = alive[q];
                     float dx = vx[v] - cx[g], dy = vy[v] - cy[g];
                     if (dx * dx + dy * dy < cm[g] * r2pm) { vwin[v] = g; break; }
                 }
@@ -500,10 +514,12 @@ static void step_arena(OracleEnv* e, int n, const float* target_xy, const int32_
         /* ---- cell eats cell (different players), all on the pre-phase snapshot ---- */
         if (K > 1) {
             for (int g = 0; g < KC; ++g) { snap_m[g] = cm[g]; gain[g] = 0.0f; win[g] = NONE; }
-            for (int j = 0; j < KC; ++j) {
-                if (!(snap_m[j] > 0.0f)) continue;
-                for (int i = 0; i < KC; ++i) {
-                    if (i / MC == j / MC || !(snap_m[i] > 0.0f)) continue;
+            na = alive_list(cm, KC, alive);
+            for (int qj = 0; qj < na; ++qj) {
+                int j = alive[qj];
+                for (int qi = 0; qi < na; ++qi) {
+                    int i = alive[qi];
+                    if (i / MC == j / MC) continue;
                     if (!(snap_m[i] >= snap_m[j] * c->eat_ratio)) continue;
                     float dx = cx[j] - cx[i], dy = cy[j] - cy[i];
                     if (dx * dx + dy * dy < snap_m[i] * r2pm) { win[j] = i; break; }
