@@ -120,6 +120,12 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
     const double box_d = (double)cfg->view_size / (double)G;  // features/extractors.py:19
     p.box = (float)box_d;
     p.hash_inv = (float)HASH_W / cfg->arena_size;
+    p.hash_bs = cfg->arena_size / (float)HASH_W;
+    {
+        int ex = 0;
+        p.box_inv = (std::frexp(p.box, &ex) == 0.5f) ? 1.0f / p.box : 0.0f;  // power of two: x * (1/box) == x / box
+        p.raster_lim = (float)(G / 2 + 1) * p.box * 1.0001f;
+    }
     for (int i = 0; i < G; ++i) p.oob_off[i] = (float)((double)(i - G / 2) * box_d);
     e->smem = smem_bytes(p.L, G);
     if (e->smem > (size_t)prop.sharedMemPerBlockOptin) {

@@ -30,6 +30,9 @@ struct DevParams {
     float box;        // (float)(view/G), the divisor of features/extractors.py:77-78
     int K, KC;
     float hash_inv;   // HASH_W / arena_size: pellet bin index = (int)(coordinate * hash_inv)
+    float hash_bs;    // arena_size / HASH_W
+    float box_inv;    // 1/box when box is a power of two (then x*box_inv == x/box exactly), else 0
+    float raster_lim; // entities farther than this from the centre on either axis cannot land in the grid
     float oob_off[128];  // (float)((double)(i - G/2) * (view/G)), features/extractors.py:87-91
 };
 
@@ -115,6 +118,13 @@ __device__ __forceinline__ bool hw_centroid(unsigned hmask, int hbase, int slot,
     unsigned alive = (__ballot_sync(hmask, m > 0.0f) >> hbase) & 0xFFFFu;
     int n = __popc(alive);
     if (n == 0) return false;
+    if (n == 1) {  // np.average over one cell is (x*m)/m: what the general path below evaluates to
+        const int src1 = hbase + __ffs(alive) - 1;
+        const float w1 = __shfl_sync(hmask, m, src1);
+        cx = (__shfl_sync(hmask, x, src1) * w1) / w1;
+        cy = (__shfl_sync(hmask, y, src1) * w1) / w1;
+        return true;
+    }
     unsigned src = __fns(alive, 0, slot + 1);
     int srcl = (slot < n) ? (int)src : 0;
     float w = __shfl_sync(hmask, m, hbase + srcl);
@@ -149,45 +159,50 @@ __device__ __forceinline__ float hw_treesum(unsigned hmask, float v) {
 struct Smem {
     float* rec;       // [words] the arena record
     int32_t* reci;    // same, as int32
-    float* tile;      // [G*G] one observation channel            (union with the hash below)
+    // pellet hash, kept through the raster
     int32_t* hstart;  // [HASH_BINS+1] first sorted position of each bin
+    uint16_t* sorted; // [P_pad]       pellet ids in bin order
+    uint16_t* extras; // [EXTRA_CAP]   pellets respawned since the hash was built (unique)
+    int32_t* isx;     // [P_pad/32+1]  bit per pellet: respawned since the hash was built
+    // union: the observation tile (only needed after the last tick) over the per-tick scratch
+    float* tile;      // [G*G] one observation channel
     int32_t* hcur;    // [HASH_BINS]   counting-sort cursors
     int32_t* pwin;    // [P_pad]       winner cell of each pellet this tick (atomicMin)
-    uint16_t* sorted; // [P_pad]       pellet ids in bin order
-    uint16_t* hits;   // [P_pad]       pellets claimed this tick
-    uint16_t* extras; // [EXTRA_CAP]   pellets respawned since the hash was built
+    uint16_t* hits;   // [P_pad]       pellets claimed this tick (bin cache while the hash is built)
     int32_t* list;    // [KC] gids of the alive cells (unordered)
     int32_t* cnt;     // [KC] pellets / foods eaten this tick
-    int32_t* eater;   // [KC] lowest-gid cell that eats this one (NONE_I between uses)
+    int32_t* eater;   // [KC] lowest-gid cell that eats this one / first virus won (NONE_I between uses)
     float* gain;      // [KC]
-    int32_t* first;   // [KC] first virus won by the cell
     int32_t* vwin;    // [V_pad]
-    float *Tx, *Ty, *dirx, *diry, *Cx, *Cy, *mass0;  // [64] each
-    int32_t *pact, *palive, *pmask;                  // [64]
-    int32_t *oobx, *ooby;                            // [128]
+    float *Tx, *Ty, *dirx, *diry, *Cx, *Cy, *mass0;  // [K_pad] each
+    int32_t *pact, *palive, *pmask;                  // [K_pad]
+    uint8_t *oobx, *ooby;                            // [128]
     int32_t* freefood;                               // [F_pad]
     int32_t* sc;                                     // [16] scalars + [32] list-membership bitmask
 };
 enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT, SC_EVCOUNT, SC_RESET, SC_ALLDONE,
-       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_ANYMULTI_START };
+       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_HASHOK };
 
-__host__ __device__ inline size_t union_words(const AgarLayout& L, int G) {
-    size_t hash = (size_t)(HASH_BINS + 1 + 3) + HASH_BINS + L.P_pad + (size_t)L.P_pad / 2 * 2 + EXTRA_CAP / 2 + 8;
-    size_t tile = (size_t)G * G;
-    size_t u = hash > tile ? hash : tile;
-    return (u + 3) & ~(size_t)3;
+__host__ __device__ inline size_t pad4z(size_t n) { return (n + 3) & ~(size_t)3; }
+__host__ __device__ inline size_t scratch_words(const AgarLayout& L) {
+    return HASH_BINS + (size_t)L.P_pad + (size_t)L.P_pad / 2 + (size_t)L.cells_total * 4;
 }
+__host__ __device__ inline size_t union_words(const AgarLayout& L, int G) {
+    size_t a = scratch_words(L), t = (size_t)G * G;
+    return pad4z(a > t ? a : t);
+}
+__host__ __device__ inline size_t kpad(const AgarLayout& L) { return pad4z((size_t)L.num_players); }
 
 __host__ __device__ inline size_t smem_bytes(const AgarLayout& L, int G) {
     size_t w = 0;
-    w += (size_t)L.words;               // rec
-    w += union_words(L, G);             // tile | hash
-    w += (size_t)L.cells_total * 5;     // list, cnt, eater, gain, first
-    w += (size_t)(L.V_pad + 4);         // vwin
-    w += 64 * 10;                       // per-player arrays
-    w += 256;                           // oobx, ooby
-    w += (size_t)(L.F_pad + 4);         // freefood
-    w += 64;                            // scalars + alive-list membership bits
+    w += (size_t)L.words;                                   // rec
+    w += HASH_BINS + 4 + pad4z((size_t)L.P_pad / 2) + EXTRA_CAP / 2 + pad4z((size_t)L.P_pad / 32 + 1);  // hash kept
+    w += union_words(L, G);                                 // tile | scratch
+    w += (size_t)(L.V_pad + 4);                             // vwin
+    w += kpad(L) * 10;                                      // per-player arrays
+    w += 64;                                                // oobx, ooby (bytes)
+    w += (size_t)(L.F_pad + 4);                             // freefood
+    w += 64;                                                // scalars + alive-list membership bits
     return w * 4 + 16;
 }
 
@@ -195,27 +210,28 @@ __device__ __forceinline__ Smem carve(float* base, const AgarLayout& L, int G) {
     Smem s;
     float* p = base;
     s.rec = p; s.reci = (int32_t*)p; p += L.words;           // words % 4 == 0
+    s.hstart = (int32_t*)p; p += HASH_BINS + 4;
+    s.sorted = (uint16_t*)p; p += pad4z((size_t)L.P_pad / 2);
+    s.extras = (uint16_t*)p; p += EXTRA_CAP / 2;
+    s.isx = (int32_t*)p; p += pad4z((size_t)L.P_pad / 32 + 1);
     s.tile = p;
     {
         int32_t* h = (int32_t*)p;
-        s.hstart = h; h += HASH_BINS + 1 + 3;
         s.hcur = h; h += HASH_BINS;
         s.pwin = h; h += L.P_pad;
-        s.sorted = (uint16_t*)h; h += L.P_pad / 2;
         s.hits = (uint16_t*)h; h += L.P_pad / 2;
-        s.extras = (uint16_t*)h;
+        s.list = h; h += L.cells_total;
+        s.cnt = h; h += L.cells_total;
+        s.eater = h; h += L.cells_total;
+        s.gain = (float*)h;
     }
     p += union_words(L, G);
-    s.list = (int32_t*)p; p += L.cells_total;
-    s.cnt = (int32_t*)p; p += L.cells_total;
-    s.eater = (int32_t*)p; p += L.cells_total;
-    s.gain = p; p += L.cells_total;
-    s.first = (int32_t*)p; p += L.cells_total;
-    s.vwin = (int32_t*)p; p += L.V_pad + 4;
-    s.Tx = p; p += 64; s.Ty = p; p += 64; s.dirx = p; p += 64; s.diry = p; p += 64;
-    s.Cx = p; p += 64; s.Cy = p; p += 64; s.mass0 = p; p += 64;
-    s.pact = (int32_t*)p; p += 64; s.palive = (int32_t*)p; p += 64; s.pmask = (int32_t*)p; p += 64;
-    s.oobx = (int32_t*)p; p += 128; s.ooby = (int32_t*)p; p += 128;
+    s.vwin = (int32_t*)p; p += L.V_pad + 4;                  // V_pad % 4 == 0
+    const size_t kp = kpad(L);
+    s.Tx = p; p += kp; s.Ty = p; p += kp; s.dirx = p; p += kp; s.diry = p; p += kp;
+    s.Cx = p; p += kp; s.Cy = p; p += kp; s.mass0 = p; p += kp;
+    s.pact = (int32_t*)p; p += kp; s.palive = (int32_t*)p; p += kp; s.pmask = (int32_t*)p; p += kp;
+    s.oobx = (uint8_t*)p; s.ooby = s.oobx + 128; p += 64;
     s.freefood = (int32_t*)p; p += L.F_pad + 4;
     s.sc = (int32_t*)p; p += 64;
     return s;
@@ -281,11 +297,14 @@ __device__ void build_hash(const DevParams& p, const Smem& s) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, P = p.c.num_pellets;
     const float* px = s.rec + L.pellet_x; const float* py = s.rec + L.pellet_y;
     for (int i = tid; i < HASH_BINS; i += nt) s.hcur[i] = 0;
+    for (int i = tid; i < L.P_pad / 32 + 1; i += nt) s.isx[i] = 0;
     __syncthreads();
     for (int i = tid; i < P; i += nt) {
-        float x = px[i];
+        const float x = px[i];
         s.pwin[i] = NONE_I;
-        if (x >= 0.0f) atomicAdd(&s.hcur[hash_coord(p, py[i]) * HASH_W + hash_coord(p, x)], 1);
+        int b = 0xFFFF;
+        if (x >= 0.0f) { b = hash_coord(p, py[i]) * HASH_W + hash_coord(p, x); atomicAdd(&s.hcur[b], 1); }
+        s.hits[i] = (uint16_t)b;  // bin cache for the scatter pass
     }
     __syncthreads();
     if (tid < 32) {
@@ -303,15 +322,12 @@ __device__ void build_hash(const DevParams& p, const Smem& s) {
 #pragma unroll
         for (int q = 0; q < PER; ++q) { s.hstart[lane * PER + q] = run; s.hcur[lane * PER + q] = run; run += c[q]; }
         if (lane == 31) s.hstart[HASH_BINS] = incl;
-        if (lane == 0) { s.sc[SC_NEXTRAS] = 0; s.sc[SC_REBUILD] = 0; s.sc[SC_NHITS] = 0; }
+        if (lane == 0) { s.sc[SC_NEXTRAS] = 0; s.sc[SC_REBUILD] = 0; s.sc[SC_NHITS] = 0; s.sc[SC_HASHOK] = 1; }
     }
     __syncthreads();
     for (int i = tid; i < P; i += nt) {
-        float x = px[i];
-        if (x >= 0.0f) {
-            int pos = atomicAdd(&s.hcur[hash_coord(p, py[i]) * HASH_W + hash_coord(p, x)], 1);
-            s.sorted[pos] = (uint16_t)i;
-        }
+        const int b = s.hits[i];
+        if (b != 0xFFFF) s.sorted[atomicAdd(&s.hcur[b], 1)] = (uint16_t)i;
     }
     __syncthreads();
 }
@@ -339,18 +355,26 @@ __device__ __forceinline__ void build_list(const DevParams& p, const Smem& s) {
     }
 }
 
+// features/extractors.py:77-78: grid index of an offset, int() truncation toward zero
+__device__ __forceinline__ int grid_bin(const DevParams& p, float d, int half) {
+    return (int)(p.box_inv != 0.0f ? d * p.box_inv : d / p.box) + half;
+}
+
 // GridFeatureExtractor.extract for every agent of the arena held in s.rec
 // (features/extractors.py:39-96; oracle_grid_extract).  obs_arena points at [A,C,G,G].
-__device__ void raster_arena(const DevParams& p, const Smem& s, float* __restrict__ obs_arena) {
+// use_hash: the pellet hash of this step is valid (pellets are then taken from the bins under
+// the view window plus the respawn list instead of scanning all of them).
+__device__ void raster_arena(const DevParams& p, const Smem& s, float* __restrict__ obs_arena, bool use_hash) {
     const AgarLayout& L = p.L;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const int hbase = lane & 16, slot = lane & 15;
     const unsigned hmask = 0xFFFFu << hbase;
     const int G = p.c.grid_size, GG = G * G, A = p.c.num_agents, K = p.K;
-    const float box = p.box, arena = p.c.arena_size, view = p.c.view_size;
+    const float arena = p.c.arena_size, lim = p.raster_lim;
     const int half = G / 2;
+    const float* px = s.rec + L.pellet_x; const float* py = s.rec + L.pellet_y;
 
-    // the tile shares its memory with the pellet hash: clear it first
+    // the tile shares its memory with the per-tick scratch: clear it first
     {
         float4* t4 = reinterpret_cast<float4*>(s.tile);
         for (int i = tid; i < GG / 4; i += nt) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -362,6 +386,9 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
         bool has = hw_centroid(hmask, hbase, slot, s.rec[L.cell_x + g], s.rec[L.cell_y + g], s.rec[L.cell_m + g], cx, cy);
         if (slot == 0) { s.Cx[k] = cx; s.Cy[k] = cy; s.palive[k] = has ? 1 : 0; }
     }
+    // write-out geometry: when 4*nt is a multiple of G a thread keeps its 4 columns and walks rows
+    const bool fast = ((4 * nt) % G) == 0;
+    const int gy_t = (4 * tid) % G, gx_t = (4 * tid) / G, rstep = (4 * nt) / G;
     __syncthreads();
 
     for (int a = 0; a < A; ++a) {
@@ -380,19 +407,45 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
             if (!(p.c.obs_flags & flag)) continue;
             bool sentinel = has;
             if (has) {
-                if (flag == AGAR_OBS_PELLETS || flag == AGAR_OBS_VIRUSES || flag == AGAR_OBS_FOODS) {
+                if (flag == AGAR_OBS_PELLETS && use_hash) {
+                    // pellets under the view window: hash rows (one warp per row), skipping entries that
+                    // respawned since the hash was built; those come from the respawn list instead
+                    const int bx0 = hash_coord(p, cx - lim), bx1 = hash_coord(p, cx + lim);
+                    const int by0 = hash_coord(p, cy - lim), by1 = hash_coord(p, cy + lim);
+                    for (int by = by0 + (tid >> 5); by <= by1; by += nt >> 5) {
+                        const int j1 = s.hstart[by * HASH_W + bx1 + 1];
+                        for (int j = s.hstart[by * HASH_W + bx0] + lane; j < j1; j += 32) {
+                            const int i = s.sorted[j];
+                            if ((s.isx[i >> 5] >> (i & 31)) & 1) continue;
+                            const float x = px[i];
+                            if (!(x >= 0.0f)) continue;
+                            const float dx = x - cx, dy = py[i] - cy;
+                            if (fabsf(dx) > lim || fabsf(dy) > lim) continue;
+                            const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
+                            if (0 <= gx && gx < G && 0 <= gy && gy < G) atomicAdd(&s.tile[gx * G + gy], 1.0f);
+                        }
+                    }
+                    const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
+                    for (int e = tid; e < nex; e += nt) {
+                        const int i = s.extras[e];
+                        const float dx = px[i] - cx, dy = py[i] - cy;
+                        if (fabsf(dx) > lim || fabsf(dy) > lim) continue;
+                        const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
+                        if (0 <= gx && gx < G && 0 <= gy && gy < G) atomicAdd(&s.tile[gx * G + gy], 1.0f);
+                    }
+                } else if (flag == AGAR_OBS_PELLETS || flag == AGAR_OBS_VIRUSES || flag == AGAR_OBS_FOODS) {
                     // point entities: value 1 each (add_ones with len(entity) <= 2); float adds of 1.0
                     // are exact, so shared-memory atomics give an order-independent count
                     const float* ex; const float* ey; int n; bool marker;
-                    if (flag == AGAR_OBS_PELLETS) { ex = s.rec + L.pellet_x; ey = s.rec + L.pellet_y; n = p.c.num_pellets; marker = true; }
+                    if (flag == AGAR_OBS_PELLETS) { ex = px; ey = py; n = p.c.num_pellets; marker = true; }
                     else if (flag == AGAR_OBS_VIRUSES) { ex = s.rec + L.virus_x; ey = s.rec + L.virus_y; n = p.c.num_viruses; marker = false; }
                     else { ex = s.rec + L.food_x; ey = s.rec + L.food_y; n = p.c.max_foods; marker = true; }
                     for (int i = tid; i < n; i += nt) {
                         float x = ex[i], y = ey[i];
                         if (marker && !(x >= 0.0f)) continue;
                         float dx = x - cx, dy = y - cy;
-                        if (fabsf(dx) > view || fabsf(dy) > view) continue;  // cannot land in the grid
-                        int gx = (int)(dx / box) + half, gy = (int)(dy / box) + half;
+                        if (fabsf(dx) > lim || fabsf(dy) > lim) continue;  // cannot land in the grid
+                        int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
                         if (0 <= gx && gx < G && 0 <= gy && gy < G) atomicAdd(&s.tile[gx * G + gy], 1.0f);
                     }
                 } else {
@@ -409,8 +462,8 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                             int bin = -1;
                             if (ok) {
                                 float dx = s.rec[L.cell_x + g] - cx, dy = s.rec[L.cell_y + g] - cy;
-                                if (!(fabsf(dx) > view || fabsf(dy) > view)) {
-                                    int gx = (int)(dx / box) + half, gy = (int)(dy / box) + half;
+                                if (!(fabsf(dx) > lim || fabsf(dy) > lim)) {
+                                    int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
                                     if (0 <= gx && gx < G && 0 <= gy && gy < G) bin = gx * G + gy;
                                 }
                             }
@@ -429,20 +482,32 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
             // write the channel out with 128-bit streaming stores and re-zero the tile
             float4* tile4 = reinterpret_cast<float4*>(s.tile);
             float4* out4 = reinterpret_cast<float4*>(out_a + (size_t)ch * GG);
-            for (int i = tid; i < GG / 4; i += nt) {
-                float4 v = tile4[i];
-                if (sentinel) {
+            const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), neg4 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+            if (!sentinel) {
+                for (int i = tid; i < GG / 4; i += nt) { __stcs(out4 + i, tile4[i]); tile4[i] = zero4; }
+            } else if (fast) {
+                const bool o0 = s.ooby[gy_t], o1 = s.ooby[gy_t + 1], o2 = s.ooby[gy_t + 2], o3 = s.ooby[gy_t + 3];
+                for (int i = tid, gx = gx_t; i < GG / 4; i += nt, gx += rstep) {
+                    float4 v = tile4[i];
+                    if (s.oobx[gx]) v = neg4;
+                    else { if (o0) v.x = -1.0f; if (o1) v.y = -1.0f; if (o2) v.z = -1.0f; if (o3) v.w = -1.0f; }
+                    __stcs(out4 + i, v);
+                    tile4[i] = zero4;
+                }
+            } else {
+                for (int i = tid; i < GG / 4; i += nt) {
+                    float4 v = tile4[i];
                     int cell = i * 4, gx = cell / G, gy = cell - gx * G;
-                    if (s.oobx[gx]) { v.x = v.y = v.z = v.w = -1.0f; }
+                    if (s.oobx[gx]) v = neg4;
                     else {
                         if (s.ooby[gy]) v.x = -1.0f;
                         if (s.ooby[gy + 1]) v.y = -1.0f;
                         if (s.ooby[gy + 2]) v.z = -1.0f;
                         if (s.ooby[gy + 3]) v.w = -1.0f;
                     }
+                    __stcs(out4 + i, v);
+                    tile4[i] = zero4;
                 }
-                __stcs(out4 + i, v);
-                tile4[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
             __syncthreads();
             ++ch;
@@ -489,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
         const float4* src = reinterpret_cast<const float4*>(a.src_state + (size_t)arena * L.words);
         float4* dst = reinterpret_cast<float4*>(s.rec);
         for (int i = tid; i < L.words / 4; i += nt) dst[i] = __ldg(src + i);
-        for (int i = tid; i < KC; i += nt) { s.cnt[i] = 0; s.eater[i] = NONE_I; s.gain[i] = 0.0f; s.first[i] = NONE_I; }
+        for (int i = tid; i < KC; i += nt) { s.cnt[i] = 0; s.eater[i] = NONE_I; s.gain[i] = 0.0f; }
         if (tid < 64) s.sc[tid] = 0;
     }
     __syncthreads();
@@ -571,38 +636,58 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
             if (act == AGAR_ACT_FEED) s.sc[SC_ANYFEED] = 1;
             if (act == AGAR_ACT_SPLIT) s.sc[SC_ANYSPLIT] = 1;
         }
-        // ---- bots: nearest pellet in the square sense window (hash neighbourhood, warp per bot),
-        //      else the roam way-point ----
-        for (int k = A + (tid >> 5); k < K; k += nt >> 5) {
-            const float Cx = s.Cx[k], Cy = s.Cy[k], R = c.bot_sense_radius;
-            const float Rp = R * 1.001f + 0.01f;
-            const int bx0 = hash_coord(p, Cx - Rp), bx1 = hash_coord(p, Cx + Rp);
-            const int by0 = hash_coord(p, Cy - Rp), by1 = hash_coord(p, Cy + Rp);
-            float best = INFINITY; int bi = NONE_I;
-            for (int by = by0; by <= by1; ++by) {
-                const int j1 = s.hstart[by * HASH_W + bx1 + 1];
-                for (int j = s.hstart[by * HASH_W + bx0] + lane; j < j1; j += 32) {
-                    const int i = s.sorted[j];
-                    float dx = px[i] - Cx, dy = py[i] - Cy;
-                    if (fabsf(dx) <= R && fabsf(dy) <= R) {
-                        float d2 = dx * dx + dy * dy;
-                        if (d2 < best || (d2 == best && i < bi)) { best = d2; bi = i; }
+        // ---- bots: nearest pellet in the square sense window, else the roam way-point.  Four lanes
+        //      per bot search the 3x3 bins around it; the result is final when it is closer than the
+        //      nearest unsearched bin edge, otherwise the whole window is searched ----
+        {
+            const unsigned qmask = 0xFu << (lane & ~3);
+            const int l4 = lane & 3;
+            for (int k = A + (tid >> 2); k < K; k += nt >> 2) {
+                const float Cx = s.Cx[k], Cy = s.Cy[k], R = c.bot_sense_radius;
+                const int bx = hash_coord(p, Cx), by = hash_coord(p, Cy);
+                int x0 = max(bx - 1, 0), x1 = min(bx + 1, HASH_W - 1), y0 = max(by - 1, 0), y1 = min(by + 1, HASH_W - 1);
+                float best = INFINITY; int bi = NONE_I;
+                for (int pass = 0; pass < 2; ++pass) {
+                    for (int row = y0; row <= y1; ++row) {
+                        const int j1 = s.hstart[row * HASH_W + x1 + 1];
+                        for (int j = s.hstart[row * HASH_W + x0] + l4; j < j1; j += 4) {
+                            const int i = s.sorted[j];
+                            float dx = px[i] - Cx, dy = py[i] - Cy;
+                            if (fabsf(dx) <= R && fabsf(dy) <= R) {
+                                float d2 = dx * dx + dy * dy;
+                                if (d2 < best || (d2 == best && i < bi)) { best = d2; bi = i; }
+                            }
+                        }
                     }
-                }
-            }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            if (lane == 0) {
-                if (bi != NONE_I) { s.Tx[k] = px[bi]; s.Ty[k] = py[bi]; }
-                else {
-                    uint32_t epoch = tick0 & ~(uint32_t)(c.bot_roam_period - 1);
-                    float x, y;
-                    rand_pos(p, gid_lo, gid_hi, (uint32_t)k, AGAR_STREAM_BOT_ROAM, epoch, x, y);
-                    s.Tx[k] = x; s.Ty[k] = y;
+                    for (int o = 2; o > 0; o >>= 1) {
+                        float ob = __shfl_xor_sync(qmask, best, o);
+                        int oi = __shfl_xor_sync(qmask, bi, o);
+                        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                    }
+                    if (pass == 1) break;
+                    // distance from the bot to the nearest edge of the searched block that has bins beyond it
+                    float margin = INFINITY;
+                    if (x0 > 0) margin = fminf(margin, Cx - (float)x0 * p.hash_bs);
+                    if (x1 < HASH_W - 1) margin = fminf(margin, (float)(x1 + 1) * p.hash_bs - Cx);
+                    if (y0 > 0) margin = fminf(margin, Cy - (float)y0 * p.hash_bs);
+                    if (y1 < HASH_W - 1) margin = fminf(margin, (float)(y1 + 1) * p.hash_bs - Cy);
+                    const float safe = margin * 0.999f - 0.01f;
+                    const bool done = (bi != NONE_I && safe > 0.0f && best < safe * safe) || safe >= R * 1.5f;
+                    if (done) break;  // uniform inside the quad (all four lanes hold the reduced result)
+                    const float Rp = R * 1.001f + 0.01f;
+                    x0 = hash_coord(p, Cx - Rp); x1 = hash_coord(p, Cx + Rp);
+                    y0 = hash_coord(p, Cy - Rp); y1 = hash_coord(p, Cy + Rp);
+                    best = INFINITY; bi = NONE_I;
+                }
+                if (l4 == 0) {
+                    if (bi != NONE_I) { s.Tx[k] = px[bi]; s.Ty[k] = py[bi]; }
+                    else {
+                        uint32_t epoch = tick0 & ~(uint32_t)(c.bot_roam_period - 1);
+                        float x, y;
+                        rand_pos(p, gid_lo, gid_hi, (uint32_t)k, AGAR_STREAM_BOT_ROAM, epoch, x, y);
+                        s.Tx[k] = x; s.Ty[k] = y;
+                    }
                 }
             }
         }
@@ -730,8 +815,10 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
                     float nx = -1.0f, ny = -1.0f;
                     if (c.pellet_regen) {
                         rand_pos(p, gid_lo, gid_hi, (uint32_t)i, AGAR_STREAM_PELLET_RESPAWN, tick, nx, ny);
-                        const int e = atomicAdd(&s.sc[SC_NEXTRAS], 1);
-                        if (e < EXTRA_CAP) s.extras[e] = (uint16_t)i; else s.sc[SC_REBUILD] = 1;
+                        if (!(atomicOr(&s.isx[i >> 5], 1 << (i & 31)) & (1 << (i & 31)))) {  // first respawn since the build
+                            const int e = atomicAdd(&s.sc[SC_NEXTRAS], 1);
+                            if (e < EXTRA_CAP) s.extras[e] = (uint16_t)i; else s.sc[SC_REBUILD] = 1;
+                        }
                     }
                     px[i] = nx; py[i] = ny;
                     if (!(a.flags & F_READONLY)) { grec[L.pellet_x + i] = nx; grec[L.pellet_y + i] = ny; }
@@ -798,7 +885,7 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
                     const int g = s.list[q];
                     if (!(cm[g] >= c.virus_pop_mass)) continue;
                     for (int v = 0; v < V; ++v)
-                        if (s.vwin[v] == g) { s.first[g] = v; break; }
+                        if (s.vwin[v] == g) { s.eater[g] = v; break; }
                 }
                 __syncthreads();
                 // one thread per player walks its slots in order (free slots are consumed sequentially
@@ -806,9 +893,9 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
                 for (int k = tid; k < K; k += nt) {
                     for (int sl = 0; sl < MC; ++sl) {
                         const int g = k * MC + sl;
-                        const int v = s.first[g];
+                        const int v = s.eater[g];
                         if (v == NONE_I) continue;
-                        s.first[g] = NONE_I;
+                        s.eater[g] = NONE_I;
                         float m1 = cm[g] + c.virus_mass;
                         int freeslot[MC]; int nfree = 0;
                         for (int q = 0; q < MC; ++q)
@@ -953,7 +1040,10 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
             s.reci[L.episode_steps] += 1;
         }
         __syncthreads();
-        if (c.auto_reset && !s.sc[SC_ALLDONE]) { reset_arena(p, s, gid_lo, gid_hi); static_dirty = true; }
+        if (c.auto_reset && !s.sc[SC_ALLDONE]) {
+            reset_arena(p, s, gid_lo, gid_hi); static_dirty = true;
+            if (tid == 0) s.sc[SC_HASHOK] = 0;  // pellets were redrawn: the raster scans them all
+        }
         if (c.event_capacity > 0 && tid == 0) a.ev_counts[arena] = s.sc[SC_EVCOUNT];
     }
 
@@ -968,7 +1058,7 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
     if ((a.flags & F_OBS) && a.obs) {
         __syncthreads();  // the tile shares memory with the pellet hash
         const int GG = c.grid_size * c.grid_size;
-        raster_arena(p, s, a.obs + (size_t)arena * A * p.C * GG);
+        raster_arena(p, s, a.obs + (size_t)arena * A * p.C * GG, s.sc[SC_HASHOK] != 0);
     }
 }
 
