@@ -155,6 +155,7 @@ __device__ __forceinline__ float hw_treesum(unsigned hmask, float v) {
 #define HASH_W 16
 #define HASH_BINS (HASH_W * HASH_W)
 #define EXTRA_CAP 64
+#define SEG_CAP 256   // bin-row segments queued per tick (overflow is scanned inline)
 
 struct Smem {
     float* rec;       // [words] the arena record
@@ -166,7 +167,8 @@ struct Smem {
     int32_t* isx;     // [P_pad/32+1]  bit per pellet: respawned since the hash was built
     // union: the observation tile (only needed after the last tick) over the per-tick scratch
     float* tile;      // [G*G] one observation channel
-    int32_t* hcur;    // [HASH_BINS]   counting-sort cursors
+    int32_t* hcur;    // [HASH_BINS]   counting-sort cursors (only while the hash is built)
+    int2* seg;        // [SEG_CAP]     per-tick work list: (cell gid, j0 | j1 << 16) runs of `sorted` to scan; same memory as hcur
     int32_t* pwin;    // [P_pad]       winner cell of each pellet this tick (atomicMin)
     uint16_t* hits;   // [P_pad]       pellets claimed this tick (bin cache while the hash is built)
     int32_t* list;    // [KC] gids of the alive cells (unordered)
@@ -178,14 +180,15 @@ struct Smem {
     int32_t *pact, *palive, *pmask;                  // [K_pad]
     uint8_t *oobx, *ooby;                            // [128]
     int32_t* freefood;                               // [F_pad]
+    int32_t* rb;                                     // [256] raster: in-view cell entities and patches
     int32_t* sc;                                     // [16] scalars + [32] list-membership bitmask
 };
 enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT, SC_EVCOUNT, SC_RESET, SC_ALLDONE,
-       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_HASHOK };
+       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NSEG, SC_NOB };
 
 __host__ __device__ inline size_t pad4z(size_t n) { return (n + 3) & ~(size_t)3; }
 __host__ __device__ inline size_t scratch_words(const AgarLayout& L) {
-    return HASH_BINS + (size_t)L.P_pad + (size_t)L.P_pad / 2 + (size_t)L.cells_total * 4;
+    return 2 * SEG_CAP + (size_t)L.P_pad + (size_t)L.P_pad / 2 + (size_t)L.cells_total * 4;  // 2*SEG_CAP >= HASH_BINS
 }
 __host__ __device__ inline size_t union_words(const AgarLayout& L, int G) {
     size_t a = scratch_words(L), t = (size_t)G * G;
@@ -202,6 +205,7 @@ __host__ __device__ inline size_t smem_bytes(const AgarLayout& L, int G) {
     w += kpad(L) * 10;                                      // per-player arrays
     w += 64;                                                // oobx, ooby (bytes)
     w += (size_t)(L.F_pad + 4);                             // freefood
+    w += 256;                                               // raster buffers
     w += 64;                                                // scalars + alive-list membership bits
     return w * 4 + 16;
 }
@@ -217,7 +221,7 @@ __device__ __forceinline__ Smem carve(float* base, const AgarLayout& L, int G) {
     s.tile = p;
     {
         int32_t* h = (int32_t*)p;
-        s.hcur = h; h += HASH_BINS;
+        s.hcur = h; s.seg = (int2*)h; h += 2 * SEG_CAP;
         s.pwin = h; h += L.P_pad;
         s.hits = (uint16_t*)h; h += L.P_pad / 2;
         s.list = h; h += L.cells_total;
@@ -233,6 +237,7 @@ __device__ __forceinline__ Smem carve(float* base, const AgarLayout& L, int G) {
     s.pact = (int32_t*)p; p += kp; s.palive = (int32_t*)p; p += kp; s.pmask = (int32_t*)p; p += kp;
     s.oobx = (uint8_t*)p; s.ooby = s.oobx + 128; p += 64;
     s.freefood = (int32_t*)p; p += L.F_pad + 4;
+    s.rb = (int32_t*)p; p += 256;
     s.sc = (int32_t*)p; p += 64;
     return s;
 }
@@ -360,10 +365,39 @@ __device__ __forceinline__ int grid_bin(const DevParams& p, float d, int half) {
     return (int)(p.box_inv != 0.0f ? d * p.box_inv : d / p.box) + half;
 }
 
+// One warp: given up to 32 in-view cell entities (key = entity order, bin, mass; bin < 0 = none)
+// one per lane, leaves in `val` the sum of the masses of all entities sharing the lane's bin,
+// accumulated in ascending key order (bit-identical to the sequential `+=` of add_ones,
+// features/extractors.py:75-82) and returns true for the lane that holds the last entity of its bin.
+__device__ __forceinline__ bool ordered_bin_sums(int key, int bin, float m, int cnt, int lane, float& val) {
+    int rank = 0;
+    for (int i = 0; i < cnt; ++i) {
+        int ki = __shfl_sync(0xffffffffu, key, i);
+        rank += (ki < key) ? 1 : 0;
+    }
+    float acc = 0.0f;
+    bool later = false;
+    for (int r = 0; r < cnt; ++r) {
+        unsigned bal = __ballot_sync(0xffffffffu, lane < cnt && rank == r);
+        int src = __ffs(bal) - 1;
+        int br = __shfl_sync(0xffffffffu, bin, src);
+        float mr = __shfl_sync(0xffffffffu, m, src);
+        if (br == bin && r <= rank) acc = acc + mr;
+        if (br == bin && r > rank) later = true;
+    }
+    val = acc;
+    return lane < cnt && bin >= 0 && !later;
+}
+
 // GridFeatureExtractor.extract for every agent of the arena held in s.rec
 // (features/extractors.py:39-96; oracle_grid_extract).  obs_arena points at [A,C,G,G].
 // use_hash: the pellet hash of this step is valid (pellets are then taken from the bins under
 // the view window plus the respawn list instead of scanning all of them).
+//
+// Count channels (pellets, viruses, foods) are binned into the shared-memory tile with exact
+// float atomics and streamed out with 128-bit stores.  Mass channels (own cells, others) hold a
+// handful of entities: the channel is stored as zeros / sentinels straight from registers and the
+// occupied bins are patched afterwards by warp 0 with sums taken in entity order.
 __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restrict__ obs_arena, bool use_hash) {
     const AgarLayout& L = p.L;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
@@ -373,6 +407,10 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
     const float arena = p.c.arena_size, lim = p.raster_lim;
     const int half = G / 2;
     const float* px = s.rec + L.pellet_x; const float* py = s.rec + L.pellet_y;
+    const float* cm = s.rec + L.cell_m; const float* cxs = s.rec + L.cell_x; const float* cys = s.rec + L.cell_y;
+    // raster buffers: others in view (unordered): key/bin/mass [32] each; patches: bin/value [2][32]
+    int* ob_key = s.rb; int* ob_bin = s.rb + 32; float* ob_m = (float*)(s.rb + 64);
+    int* pt_bin = s.rb + 96; float* pt_val = (float*)(s.rb + 160);  // [2*32] each: own cells then others
 
     // the tile shares its memory with the per-tick scratch: clear it first
     {
@@ -383,30 +421,85 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
     for (int g = tid; g < A * MC; g += nt) {
         int k = g >> 4;
         float cx = 0.0f, cy = 0.0f;
-        bool has = hw_centroid(hmask, hbase, slot, s.rec[L.cell_x + g], s.rec[L.cell_y + g], s.rec[L.cell_m + g], cx, cy);
+        bool has = hw_centroid(hmask, hbase, slot, cxs[g], cys[g], cm[g], cx, cy);
         if (slot == 0) { s.Cx[k] = cx; s.Cy[k] = cy; s.palive[k] = has ? 1 : 0; }
     }
+    if (tid == 0) s.sc[SC_NOB] = 0;
     // write-out geometry: when 4*nt is a multiple of G a thread keeps its 4 columns and walks rows
     const bool fast = ((4 * nt) % G) == 0;
     const int gy_t = (4 * tid) % G, gx_t = (4 * tid) / G, rstep = (4 * nt) / G;
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), neg4 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
     __syncthreads();
 
     for (int a = 0; a < A; ++a) {
         const float cx = s.Cx[a], cy = s.Cy[a];
         const bool has = s.palive[a] != 0;
         float* out_a = obs_arena + (size_t)a * p.C * GG;
-        // per-row / per-column out-of-bounds flags (add_out_of_bounds, features/extractors.py:84-96)
+        // ---- gather phase: out-of-bounds flags, in-view cell entities ----
         for (int i = tid; i < G; i += nt) {
             float xl = p.oob_off[i] + cx, yl = p.oob_off[i] + cy;
             s.oobx[i] = !(0.0f <= xl && xl < arena);
             s.ooby[i] = !(0.0f <= yl && yl < arena);
         }
-        int ch = 0;
+        if (has && (p.c.obs_flags & AGAR_OBS_OTHERS)) {
+            for (int g = tid; g < p.KC; g += nt) {
+                const float m = cm[g];
+                if (!(m > 0.0f) || (g >> 4) == a) continue;
+                const float dx = cxs[g] - cx, dy = cys[g] - cy;
+                if (fabsf(dx) > lim || fabsf(dy) > lim) continue;
+                const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
+                if (0 <= gx && gx < G && 0 <= gy && gy < G) {
+                    const int e = atomicAdd(&s.sc[SC_NOB], 1);
+                    if (e < 32) { ob_key[e] = g; ob_bin[e] = gx * G + gy; ob_m[e] = m; }
+                }
+            }
+        }
+        __syncthreads();
+        const int nob = s.sc[SC_NOB];
+        const bool others_tile = nob > 32;  // more cells in view than one warp holds: use the tile path
+        // ---- warp 0: ordered sums for the own-cells and others channels -> patch lists ----
+        if (tid < 32) {
+            pt_bin[lane] = -1; pt_bin[32 + lane] = -1;
+            if (has && (p.c.obs_flags & AGAR_OBS_CELLS)) {
+                const int g = a * MC + lane;
+                const float m = (lane < MC) ? cm[g] : 0.0f;
+                int bin = -1;
+                if (m > 0.0f) {
+                    const float dx = cxs[g] - cx, dy = cys[g] - cy;
+                    if (!(fabsf(dx) > lim || fabsf(dy) > lim)) {
+                        const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
+                        if (0 <= gx && gx < G && 0 <= gy && gy < G) bin = gx * G + gy;
+                    }
+                }
+                const unsigned inb = __ballot_sync(0xffffffffu, bin >= 0);
+                if (__popc(inb) == 1) {  // a single cell in view: 0 + m
+                    if (bin >= 0) { pt_bin[lane] = bin; pt_val[lane] = m; }
+                } else if (inb) {
+                    float val;
+                    if (ordered_bin_sums(lane, bin, m, MC, lane, val)) { pt_bin[lane] = bin; pt_val[lane] = val; }
+                }
+            }
+            if (has && (p.c.obs_flags & AGAR_OBS_OTHERS) && nob > 0 && !others_tile) {
+                const int key = lane < nob ? ob_key[lane] : NONE_I;
+                const int bin = lane < nob ? ob_bin[lane] : -1;
+                const float m = lane < nob ? ob_m[lane] : 0.0f;
+                float val = m;
+                if (nob == 1 ? lane == 0 : ordered_bin_sums(key, bin, m, nob, lane, val)) { pt_bin[32 + lane] = bin; pt_val[32 + lane] = val; }
+            }
+        }
+        // ---- channels ----
+        int ch = 0, ch_cells = -1, ch_others = -1;
         for (int bit = 0; bit < 5; ++bit) {
             const int flag = 1 << bit;
             if (!(p.c.obs_flags & flag)) continue;
+            float4* out4 = reinterpret_cast<float4*>(out_a + (size_t)ch * GG);
             bool sentinel = has;
-            if (has) {
+            if (flag == AGAR_OBS_OTHERS) sentinel = has && K > 1;
+            const bool mass = flag == AGAR_OBS_CELLS || flag == AGAR_OBS_OTHERS;
+            if (flag == AGAR_OBS_CELLS) ch_cells = ch;
+            if (flag == AGAR_OBS_OTHERS) ch_others = ch;
+            const bool via_tile = !mass || (flag == AGAR_OBS_OTHERS && others_tile);
+            if (via_tile && has) {
                 if (flag == AGAR_OBS_PELLETS && use_hash) {
                     // pellets under the view window: hash rows (one warp per row), skipping entries that
                     // respawned since the hash was built; those come from the respawn list instead
@@ -433,7 +526,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                         const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
                         if (0 <= gx && gx < G && 0 <= gy && gy < G) atomicAdd(&s.tile[gx * G + gy], 1.0f);
                     }
-                } else if (flag == AGAR_OBS_PELLETS || flag == AGAR_OBS_VIRUSES || flag == AGAR_OBS_FOODS) {
+                } else if (!mass) {
                     // point entities: value 1 each (add_ones with len(entity) <= 2); float adds of 1.0
                     // are exact, so shared-memory atomics give an order-independent count
                     const float* ex; const float* ey; int n; bool marker;
@@ -448,70 +541,102 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                         int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
                         if (0 <= gx && gx < G && 0 <= gy && gy < G) atomicAdd(&s.tile[gx * G + gy], 1.0f);
                     }
-                } else {
-                    // cell rows: value = mass, accumulated strictly in entity order (own: slot order;
-                    // others: player order then slot order) by warp 0
-                    if (flag == AGAR_OBS_OTHERS) sentinel = K > 1;
-                    if (tid < 32) {
-                        const int g0 = (flag == AGAR_OBS_CELLS) ? a * MC : 0;
-                        const int g1 = (flag == AGAR_OBS_CELLS) ? a * MC + MC : p.KC;
-                        for (int base = g0; base < g1; base += 32) {
-                            int g = base + lane;
-                            float m = (g < g1) ? s.rec[L.cell_m + g] : 0.0f;
-                            bool ok = m > 0.0f && ((flag == AGAR_OBS_CELLS) || (g >> 4) != a);
-                            int bin = -1;
-                            if (ok) {
-                                float dx = s.rec[L.cell_x + g] - cx, dy = s.rec[L.cell_y + g] - cy;
-                                if (!(fabsf(dx) > lim || fabsf(dy) > lim)) {
-                                    int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
-                                    if (0 <= gx && gx < G && 0 <= gy && gy < G) bin = gx * G + gy;
-                                }
+                } else if (tid < 32) {
+                    // others, crowded view: masses accumulated strictly in (player, slot) order by warp 0
+                    for (int base = 0; base < p.KC; base += 32) {
+                        int g = base + lane;
+                        float m = (g < p.KC) ? cm[g] : 0.0f;
+                        int bin = -1;
+                        if (m > 0.0f && (g >> 4) != a) {
+                            float dx = cxs[g] - cx, dy = cys[g] - cy;
+                            if (!(fabsf(dx) > lim || fabsf(dy) > lim)) {
+                                int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
+                                if (0 <= gx && gx < G && 0 <= gy && gy < G) bin = gx * G + gy;
                             }
-                            unsigned mask = __ballot_sync(0xffffffffu, bin >= 0);
-                            while (mask) {
-                                int src = __ffs(mask) - 1;
-                                if (lane == src) s.tile[bin] = s.tile[bin] + m;
-                                __syncwarp();
-                                mask &= mask - 1;
-                            }
+                        }
+                        unsigned mask = __ballot_sync(0xffffffffu, bin >= 0);
+                        while (mask) {
+                            int src = __ffs(mask) - 1;
+                            if (lane == src) s.tile[bin] = s.tile[bin] + m;
+                            __syncwarp();
+                            mask &= mask - 1;
                         }
                     }
                 }
             }
-            __syncthreads();
-            // write the channel out with 128-bit streaming stores and re-zero the tile
-            float4* tile4 = reinterpret_cast<float4*>(s.tile);
-            float4* out4 = reinterpret_cast<float4*>(out_a + (size_t)ch * GG);
-            const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), neg4 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
-            if (!sentinel) {
-                for (int i = tid; i < GG / 4; i += nt) { __stcs(out4 + i, tile4[i]); tile4[i] = zero4; }
-            } else if (fast) {
-                const bool o0 = s.ooby[gy_t], o1 = s.ooby[gy_t + 1], o2 = s.ooby[gy_t + 2], o3 = s.ooby[gy_t + 3];
-                for (int i = tid, gx = gx_t; i < GG / 4; i += nt, gx += rstep) {
-                    float4 v = tile4[i];
-                    if (s.oobx[gx]) v = neg4;
-                    else { if (o0) v.x = -1.0f; if (o1) v.y = -1.0f; if (o2) v.z = -1.0f; if (o3) v.w = -1.0f; }
-                    __stcs(out4 + i, v);
-                    tile4[i] = zero4;
-                }
-            } else {
-                for (int i = tid; i < GG / 4; i += nt) {
-                    float4 v = tile4[i];
-                    int cell = i * 4, gx = cell / G, gy = cell - gx * G;
-                    if (s.oobx[gx]) v = neg4;
-                    else {
-                        if (s.ooby[gy]) v.x = -1.0f;
-                        if (s.ooby[gy + 1]) v.y = -1.0f;
-                        if (s.ooby[gy + 2]) v.z = -1.0f;
-                        if (s.ooby[gy + 3]) v.w = -1.0f;
+            if (via_tile) {
+                __syncthreads();
+                // write the channel out with 128-bit streaming stores and re-zero the tile
+                float4* tile4 = reinterpret_cast<float4*>(s.tile);
+                if (!sentinel) {
+                    for (int i = tid; i < GG / 4; i += nt) { __stcs(out4 + i, tile4[i]); tile4[i] = zero4; }
+                } else if (fast) {
+                    const bool o0 = s.ooby[gy_t], o1 = s.ooby[gy_t + 1], o2 = s.ooby[gy_t + 2], o3 = s.ooby[gy_t + 3];
+                    for (int i = tid, gx = gx_t; i < GG / 4; i += nt, gx += rstep) {
+                        float4 v = tile4[i];
+                        if (s.oobx[gx]) v = neg4;
+                        else { if (o0) v.x = -1.0f; if (o1) v.y = -1.0f; if (o2) v.z = -1.0f; if (o3) v.w = -1.0f; }
+                        __stcs(out4 + i, v);
+                        tile4[i] = zero4;
                     }
-                    __stcs(out4 + i, v);
-                    tile4[i] = zero4;
+                } else {
+                    for (int i = tid; i < GG / 4; i += nt) {
+                        float4 v = tile4[i];
+                        int cell = i * 4, gx = cell / G, gy = cell - gx * G;
+                        if (s.oobx[gx]) v = neg4;
+                        else {
+                            if (s.ooby[gy]) v.x = -1.0f;
+                            if (s.ooby[gy + 1]) v.y = -1.0f;
+                            if (s.ooby[gy + 2]) v.z = -1.0f;
+                            if (s.ooby[gy + 3]) v.w = -1.0f;
+                        }
+                        __stcs(out4 + i, v);
+                        tile4[i] = zero4;
+                    }
+                }
+                __syncthreads();
+            } else {
+                // mass channel: zeros / sentinels straight from registers; occupied bins are patched below
+                if (!sentinel) {
+                    for (int i = tid; i < GG / 4; i += nt) __stcs(out4 + i, zero4);
+                } else if (fast) {
+                    float4 row = zero4;
+                    if (s.ooby[gy_t]) row.x = -1.0f;
+                    if (s.ooby[gy_t + 1]) row.y = -1.0f;
+                    if (s.ooby[gy_t + 2]) row.z = -1.0f;
+                    if (s.ooby[gy_t + 3]) row.w = -1.0f;
+                    for (int i = tid, gx = gx_t; i < GG / 4; i += nt, gx += rstep) __stcs(out4 + i, s.oobx[gx] ? neg4 : row);
+                } else {
+                    for (int i = tid; i < GG / 4; i += nt) {
+                        float4 v = zero4;
+                        int cell = i * 4, gx = cell / G, gy = cell - gx * G;
+                        if (s.oobx[gx]) v = neg4;
+                        else {
+                            if (s.ooby[gy]) v.x = -1.0f;
+                            if (s.ooby[gy + 1]) v.y = -1.0f;
+                            if (s.ooby[gy + 2]) v.z = -1.0f;
+                            if (s.ooby[gy + 3]) v.w = -1.0f;
+                        }
+                        __stcs(out4 + i, v);
+                    }
                 }
             }
-            __syncthreads();
             ++ch;
         }
+        // ---- patches: the bulk stores above must be ordered before them ----
+        __syncthreads();
+        if (tid < 64 && has) {
+            const int which = tid >> 5;  // 0: own cells, 1: others
+            const int chn = which ? ch_others : ch_cells;
+            const int bin = pt_bin[tid];
+            if (chn >= 0 && bin >= 0 && !(which && others_tile)) {
+                const int gx = bin / G, gy = bin - gx * G;
+                const bool sent = which ? (K > 1) : true;
+                if (!(sent && (s.oobx[gx] || s.ooby[gy]))) out_a[(size_t)chn * GG + bin] = pt_val[tid];
+            }
+        }
+        if (tid == 0) s.sc[SC_NOB] = 0;
+        __syncthreads();
     }
 }
 
@@ -752,7 +877,8 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
         for (int tk = 0; tk < c.ticks_per_step; ++tk) {
             const uint32_t tick = tick0 + (uint32_t)tk;
             if (s.sc[SC_REBUILD]) build_hash(p, s);  // too many respawns since the last build (uniform)
-            // ---- motion + pellet query: one thread per alive cell ----
+            // ---- motion: one thread per alive cell; it queues the runs of the pellet hash under the
+            //      cell's (padded) bounding box as segments and checks the few respawned pellets itself ----
             {
                 const int n = s.sc[SC_NLIST];
                 const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
@@ -776,13 +902,15 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
                     cx[g] = x; cy[g] = y; cix[g] = ix; ciy[g] = iy;
                     float t = ct[g];
                     if (t > 0.0f) ct[g] = t - 1.0f;
-                    // pellets whose centre lies inside the disc: bins overlapped by the (padded) bounding box
                     const float rp = r * 1.001f + 0.01f;
                     const int bx0 = hash_coord(p, x - rp), bx1 = hash_coord(p, x + rp);
                     const int by0 = hash_coord(p, y - rp), by1 = hash_coord(p, y + rp);
                     for (int by = by0; by <= by1; ++by) {
-                        const int j1 = s.hstart[by * HASH_W + bx1 + 1];
-                        for (int j = s.hstart[by * HASH_W + bx0]; j < j1; ++j) {
+                        const int j0 = s.hstart[by * HASH_W + bx0], j1 = s.hstart[by * HASH_W + bx1 + 1];
+                        if (j1 <= j0) continue;
+                        const int si = atomicAdd(&s.sc[SC_NSEG], 1);
+                        if (si < SEG_CAP) { s.seg[si] = make_int2(g, j0 | (j1 << 16)); continue; }
+                        for (int j = j0; j < j1; ++j) {  // work list full: scan the run here
                             const int i = s.sorted[j];
                             const float qx = px[i];
                             if (!(qx >= 0.0f)) continue;
@@ -801,6 +929,26 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
                 for (int f = tid; f < F; f += nt)
                     if (fx[f] >= 0.0f) s.sc[SC_FOODANY] = 1;
                 for (int v = tid; v < V; v += nt) s.vwin[v] = NONE_I;
+            }
+            __syncthreads();
+            // ---- pellet query: groups of 8 lanes scan the queued segments; a pellet whose centre lies
+            //      inside the disc is claimed with atomicMin (lowest gid wins) ----
+            {
+                const int nseg = min(s.sc[SC_NSEG], SEG_CAP);
+                const int l8 = tid & 7;
+                for (int sgi = tid >> 3; sgi < nseg; sgi += nt >> 3) {
+                    const int2 sg = s.seg[sgi];
+                    const int g = sg.x, j1 = (int)((unsigned)sg.y >> 16);
+                    const float x = cx[g], y = cy[g], r2 = cm[g] * r2pm;
+                    for (int j = (sg.y & 0xFFFF) + l8; j < j1; j += 8) {
+                        const int i = s.sorted[j];
+                        const float qx = px[i];
+                        if (!(qx >= 0.0f)) continue;
+                        const float ex = qx - x, ey = py[i] - y;
+                        if (ex * ex + ey * ey < r2)
+                            if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
+                    }
+                }
             }
             __syncthreads();
             // ---- resolve the claimed pellets: winner = lowest gid (atomicMin), respawn by Philox ----
@@ -875,7 +1023,7 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
                         }
                     }
                 }
-                if (tid == 0) { s.sc[SC_NHITS] = 0; s.sc[SC_FOODANY] = 0; }
+                if (tid == 0) { s.sc[SC_NHITS] = 0; s.sc[SC_FOODANY] = 0; s.sc[SC_NSEG] = 0; }
             }
             __syncthreads();
             // ---- virus pops ----
@@ -930,22 +1078,29 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
             }
             // ---- cell eats cell (different players) on the pre-phase snapshot ----
             if (K > 1) {
+                // four lanes per prey, each scanning a quarter of the possible eaters; lowest gid wins
                 const int n = s.sc[SC_NLIST];
-                for (int q = tid; q < n; q += nt) {
+                const unsigned qmask = 0xFu << (lane & ~3);
+                const int l4 = lane & 3;
+                for (int q = tid >> 2; q < n; q += nt >> 2) {
                     const int j = s.list[q];
                     const float mj = cm[j];
-                    if (!(mj > 0.0f)) continue;
                     const float need = mj * c.eat_ratio, x = cx[j], y = cy[j];
                     const int kj = j >> 4;
                     int best = NONE_I;
-                    for (int qi = 0; qi < n; ++qi) {
-                        const int i = s.list[qi];
-                        const float mi = cm[i];
-                        if ((i >> 4) == kj || !(mi >= need)) continue;  // need > 0, so dead cells fail here
-                        const float dx = x - cx[i], dy = y - cy[i];
-                        if (dx * dx + dy * dy < mi * r2pm && i < best) best = i;
+                    if (mj > 0.0f) {
+#pragma unroll 4
+                        for (int qi = l4; qi < n; qi += 4) {
+                            const int i = s.list[qi];
+                            const float mi = cm[i];
+                            if ((i >> 4) == kj || !(mi >= need)) continue;  // need > 0, so dead cells fail here
+                            const float dx = x - cx[i], dy = y - cy[i];
+                            if (dx * dx + dy * dy < mi * r2pm && i < best) best = i;
+                        }
                     }
-                    if (best != NONE_I) { s.eater[j] = best; s.sc[SC_ANYEAT] = 1; }
+                    best = min(best, __shfl_xor_sync(qmask, best, 1));
+                    best = min(best, __shfl_xor_sync(qmask, best, 2));
+                    if (l4 == 0 && best != NONE_I) { s.eater[j] = best; s.sc[SC_ANYEAT] = 1; }
                 }
                 __syncthreads();
                 if (s.sc[SC_ANYEAT]) {
