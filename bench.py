@@ -30,14 +30,25 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ARENAS_PER_GPU = 4096
-WORLD = dict(num_agents=1, num_bots=25, num_viruses=25, num_pellets=1000, arena_size=500.0, ticks_per_step=4,
-             grid_size=64, obs_flags=7, pellet_regen=1, auto_reset=1, max_foods=64)
+WORLDS = {
+    # BASELINE.json configs[1] (the headline): viruses + bot opponents (a2c/train.py:19-27 values)
+    "cfg2": dict(num_agents=1, num_bots=25, num_viruses=25, num_pellets=1000, arena_size=500.0, ticks_per_step=4,
+                 grid_size=64, obs_flags=7, pellet_regen=1, auto_reset=1, max_foods=64),
+    # configs[0]/[2]/[4] world: single agent, pellets only (ppo.textproto:6-12 with num_agents 1)
+    "cfg1": dict(num_agents=1, num_bots=0, num_viruses=0, num_pellets=1000, arena_size=1000.0, ticks_per_step=4,
+                 grid_size=64, obs_flags=7, pellet_regen=1, auto_reset=1, max_foods=64),
+    # configs[3] world: 16 agents per arena with split/merge (ppo.textproto:4-23)
+    "cfg4": dict(num_agents=16, num_bots=0, num_viruses=0, num_pellets=1000, arena_size=1000.0, ticks_per_step=4,
+                 grid_size=64, obs_flags=7, pellet_regen=1, auto_reset=1, max_foods=64),
+}
+WORLD = WORLDS["cfg2"]
 METRIC = "env_steps_per_sec_incl_grid_obs"
 UNIT = "env-steps/s"
 
 
-def algorithmic_bytes_per_env_step(w=WORLD):
+def algorithmic_bytes_per_env_step(w=None):
     """compulsory HBM traffic of one env step (state touched once, obs written)."""
+    w = w or WORLD
     P, V, F, A = w["num_pellets"], w["num_viruses"], w["max_foods"], w["num_agents"]
     K = A + w["num_bots"]
     C = bin(w["obs_flags"]).count("1")
@@ -105,7 +116,7 @@ def cpu_arm(arenas, steps, warmup, nthreads, seed=0):
     rng = np.random.default_rng(seed)
     times = []
     for i in range(warmup + steps):
-        idx = rng.integers(0, len(act_tab), size=(arenas, 1))
+        idx = rng.integers(0, len(act_tab), size=(arenas, WORLD["num_agents"]))
         t0 = time.perf_counter()
         env.step(xy_tab[idx], act_tab[idx], out=obs)
         if i >= warmup:
@@ -128,7 +139,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: 1 agent + 25 bots + 25 viruses, 1000 pellets, arena 500, obs 3x64x64 f32",
+        "config": {"workload": f"{args.world}: {WORLD['num_agents']} agent(s) + {WORLD['num_bots']} bots + "
+                               f"{WORLD['num_viruses']} viruses, {WORLD['num_pellets']} pellets, arena "
+                               f"{WORLD['arena_size']:g}, obs 3x64x64 f32 per agent",
                    "arenas_per_step": sample, **WORLD},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} arenas x {args.steps} steps (of the {ARENAS_PER_GPU}-arena workload), "
@@ -160,7 +173,8 @@ def run_cuda(args):
     env = ab.BatchedAgarioEnv(cfg, device=dev, seed=args.seed, action_config=ac)
     K, W = args.steps, max(args.warmup, 3)
     gen = torch.Generator(device=dev); gen.manual_seed(args.seed + rank)
-    idx = torch.randint(0, env.num_actions, (K + W, N, 1), generator=gen, device=dev, dtype=torch.int32)
+    A = WORLD["num_agents"]
+    idx = torch.randint(0, env.num_actions, (K + W, N, A), generator=gen, device=dev, dtype=torch.int32)
     obs = [torch.empty(env.obs_shape, dtype=torch.float32, device=dev) for _ in range(2)]
     env.reset(out_obs=obs[0])
 
@@ -195,12 +209,12 @@ def run_cuda(args):
     # ---- e2e: host buffers through agar_step_host (H2D actions, D2H obs/reward/done inside) ----
     xy_tab, act_tab = ab.ppo_action_table(ac)
     Ke = max(2, min(K, args.e2e_steps))
-    h_idx = idx[W:W + Ke].cpu().numpy()[..., 0]
-    h_xy = torch.from_numpy(np.ascontiguousarray(xy_tab[h_idx][:, :, None, :])).pin_memory()   # [Ke,N,1,2]
-    h_act = torch.from_numpy(np.ascontiguousarray(act_tab[h_idx][:, :, None])).pin_memory()    # [Ke,N,1]
+    h_idx = idx[W:W + Ke].cpu().numpy()
+    h_xy = torch.from_numpy(np.ascontiguousarray(xy_tab[h_idx])).pin_memory()   # [Ke,N,A,2]
+    h_act = torch.from_numpy(np.ascontiguousarray(act_tab[h_idx])).pin_memory()  # [Ke,N,A]
     h_obs = torch.empty(env.obs_shape, dtype=torch.float32).pin_memory()
-    h_rew = torch.empty((N, 1), dtype=torch.float32).pin_memory()
-    h_done = torch.empty((N, 1), dtype=torch.uint8).pin_memory()
+    h_rew = torch.empty((N, A), dtype=torch.float32).pin_memory()
+    h_done = torch.empty((N, A), dtype=torch.uint8).pin_memory()
     env.step_host(h_xy[0].numpy(), h_act[0].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())  # warm-up
     barrier()
     t0 = time.perf_counter()
@@ -211,8 +225,8 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * N * Ke / float(te.item())
-    h2d = N * 1 * (8 + 4)
-    d2h = h_obs.numel() * 4 + N * 1 * (4 + 1)
+    h2d = N * A * (8 + 4)
+    d2h = h_obs.numel() * 4 + N * A * (4 + 1)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -223,10 +237,14 @@ def run_cuda(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: 4096 arenas/GPU, 1 agent + 25 bots + 25 viruses, 1000 pellets, arena 500, "
-                                   "obs 3x64x64 f32, random policy over 25 actions (8 dirs, split, feed)",
-                       "arenas_per_gpu": N, "l2": "no flush needed: each step streams the 79 MB state and writes a "
-                                                  "201 MB observation buffer (2 alternate) > 126 MB L2", **WORLD},
+            "config": {"workload": f"{args.world}: {N} arenas/GPU, {A} agent(s) + {WORLD['num_bots']} bots + "
+                                   f"{WORLD['num_viruses']} viruses, {WORLD['num_pellets']} pellets, arena "
+                                   f"{WORLD['arena_size']:g}, obs 3x64x64 f32 per agent, random policy over 25 actions "
+                                   "(8 dirs, split, feed)",
+                       "arenas_per_gpu": N,
+                       "l2": f"no flush: each step streams {env.layout.words * 4 * N / 1e6:.0f} MB of state and writes "
+                             f"a {obs[0].numel() * 4 / 1e6:.0f} MB observation buffer (2 alternate); L2 is 126 MB",
+                       **WORLD},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "api": "agar_step_host (pinned host buffers; obs D2H every step)"},
@@ -260,7 +278,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--world", default="cfg2", choices=sorted(WORLDS), help="BASELINE.json world (default: the headline cfg2)")
     args = ap.parse_args()
+    global WORLD
+    WORLD = WORLDS[args.world]
     if args.impl == "reference":
         run_reference(args)
     else:
