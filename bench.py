@@ -156,6 +156,7 @@ def run_cuda(args):
     import torch
     import torch.distributed as dist
     import agarai_b200 as ab
+    from agarai_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -169,7 +170,8 @@ def run_cuda(args):
 
     N = args.arenas
     ac = ab.ActionConfig(8, 1, True, True)
-    cfg = ab.default_config(num_arenas=N, arena_id_base=rank * N, **WORLD)
+    shard = sharding.shard_from_env(N)  # rank r owns global arenas [r*N, (r+1)*N): no data-path collective
+    cfg = ab.default_config(num_arenas=N, arena_id_base=shard.arena_id_base, **WORLD)
     env = ab.BatchedAgarioEnv(cfg, device=dev, seed=args.seed, action_config=ac)
     K, W = args.steps, max(args.warmup, 3)
     gen = torch.Generator(device=dev); gen.manual_seed(args.seed + rank)
@@ -200,10 +202,7 @@ def run_cuda(args):
     ms = e0.elapsed_time(e1)
     launches = env.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = sharding.max_over_ranks(ms, dev)
     value = world * N * K / (ms_max * 1e-3)
 
     # ---- e2e: host buffers through agar_step_host (H2D actions, D2H obs/reward/done inside) ----
@@ -221,10 +220,7 @@ def run_cuda(args):
     for i in range(Ke):
         env.step_host(h_xy[i].numpy(), h_act[i].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())
     torch.cuda.synchronize(dev)
-    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * Ke / float(te.item())
+    e2e_value = world * N * Ke / sharding.max_over_ranks(time.perf_counter() - t0, dev)
     h2d = N * A * (8 + 4)
     d2h = h_obs.numel() * 4 + N * A * (4 + 1)
 

@@ -327,3 +327,27 @@ def test_large_batch_properties(oracle):
         assert np.array_equal(oenv.get_state().view(np.int32), st[n:n + 1].cpu().numpy().view(np.int32))
         assert np.array_equal(o_o[0], obs[n].cpu().numpy()) and o_r[0, 0] == float(rew[n, 0])
     env.close()
+
+
+def test_ppo_loop_runs_and_snapshots_rerasterise_exactly(oracle):
+    """configs[2] shape at test size: rollout with GAE on the GPU, SGD on minibatches whose
+    observations are re-rasterised from state snapshots; the re-rasterised observations equal the
+    ones the step produced."""
+    import agarai_b200 as ab
+    from agarai_b200 import ppo
+    env = ab.BatchedAgarioEnv(ab.default_config(num_arenas=32, num_agents=1, obs_flags=7, auto_reset=1,
+                                                arena_size=200.0, num_pellets=300, grid_size=32), seed=3,
+                              action_config=ab.ActionConfig(8, 1))
+    tr = ppo.PPOTrainer(env, ppo.PPOConfig(episode_length=16, num_sgd_steps=2, batch_size=64, num_features=64), seed=0)
+    s0 = env.get_state()
+    assert torch.equal(env.observe_records(s0), tr.obs)          # snapshot -> same observation as reset gave
+    stats = tr.train_episode()
+    assert np.isfinite(stats["loss"]) and tr.sgd_steps == 2
+    assert tr.roll["rewards"].shape == (16, 32) and tr.roll["values"].shape == (17, 32)
+    adv, ret = tr.advantages()
+    oadv, oret = oracle.gae(tr.roll["rewards"].cpu().numpy(), tr.roll["values"].cpu().numpy(), 0.75, 0.1,
+                            done=tr.roll["dones"].cpu().numpy(), end_value=tr.roll["values"][-1].cpu().numpy())
+    assert np.array_equal(adv.cpu().numpy(), oadv) and np.array_equal(ret.cpu().numpy(), oret)
+    stats2 = tr.train_episode()
+    assert np.isfinite(stats2["loss"]) and tr.sgd_steps == 4
+    env.close()
