@@ -162,7 +162,7 @@ class PPOTrainer:
             nn.utils.clip_grad_norm_(self.model.parameters(), cfg.grad_clip)
             self.opt.step(); self.sched.step()
             self.sgd_steps += 1
-            stats = {"loss": float(loss), "actor": float(la), "critic": float(lc), "entropy": float(ent)}
+            stats = {"loss": loss.item(), "actor": la.item(), "critic": lc.item(), "entropy": ent.item()}
         return stats
 
     def train_episode(self):
