@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -37,6 +38,7 @@ struct AgarEnv {
     float* d_state = nullptr;
     int32_t* d_events = nullptr;
     int32_t* d_ev_counts = nullptr;
+    int32_t* d_hash = nullptr;  // persisted pellet hash, one record per arena (derived data, not state)
     float* d_tab_xy = nullptr;
     int32_t* d_tab_act = nullptr;
     int32_t n_actions = 0;
@@ -70,6 +72,7 @@ KArgs base_args(AgarEnv* e) {
     a.src_state = e->d_state;
     a.events = e->d_events;
     a.ev_counts = e->d_ev_counts;
+    a.hash = std::getenv("AGAR_NO_PERSIST") ? nullptr : e->d_hash;  // debug switch: rebuild the pellet hash every step
     return a;
 }
 
@@ -136,6 +139,10 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
     const size_t state_bytes = (size_t)cfg->num_arenas * p.L.words * sizeof(float);
     CUDA_OK(cudaMalloc(&e->d_state, state_bytes));
     CUDA_OK(cudaMemset(e->d_state, 0, state_bytes));
+    p.hash_words = (int)hash_record_words(p.L);
+    p.hash_epoch = 1;
+    CUDA_OK(cudaMalloc(&e->d_hash, (size_t)cfg->num_arenas * p.hash_words * sizeof(int32_t)));
+    CUDA_OK(cudaMemset(e->d_hash, 0, (size_t)cfg->num_arenas * p.hash_words * sizeof(int32_t)));  // epoch 0 = stale
     if (cfg->event_capacity > 0) {
         CUDA_OK(cudaMalloc(&e->d_events, (size_t)cfg->num_arenas * cfg->event_capacity * 4 * sizeof(int32_t)));
         CUDA_OK(cudaMalloc(&e->d_ev_counts, (size_t)cfg->num_arenas * sizeof(int32_t)));
@@ -148,7 +155,7 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
 int agar_destroy(AgarEnv* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
-    cudaFree(e->d_state); cudaFree(e->d_events); cudaFree(e->d_ev_counts);
+    cudaFree(e->d_state); cudaFree(e->d_events); cudaFree(e->d_ev_counts); cudaFree(e->d_hash);
     cudaFree(e->d_tab_xy); cudaFree(e->d_tab_act);
     cudaFree(e->d_target); cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_reward); cudaFree(e->d_done);
     if (e->host_stream) cudaStreamDestroy(e->host_stream);
@@ -173,6 +180,7 @@ int agar_seed(AgarEnv* e, uint64_t seed) {
     CUDA_OK(cudaSetDevice(e->device));
     e->p.seed_lo = (uint32_t)seed;
     e->p.seed_hi = (uint32_t)(seed >> 32);
+    e->p.hash_epoch += 1;  // conservative: persisted hashes are rebuilt
     // tick counters restart from 0: one strided 4-byte memset per arena record
     CUDA_OK(cudaMemset2D(e->d_state + e->p.L.tick, (size_t)e->p.L.words * sizeof(float), 0, sizeof(int32_t),
                          (size_t)e->p.c.num_arenas));
@@ -182,6 +190,7 @@ int agar_seed(AgarEnv* e, uint64_t seed) {
 int agar_reset(AgarEnv* e, const uint8_t* d_reset_mask, float* d_obs, void* stream) {
     if (!e) return fail("env is NULL");
     CUDA_OK(cudaSetDevice(e->device));
+    e->p.hash_epoch += 1;  // pellets are redrawn: persisted hashes are stale
     KArgs a = base_args(e);
     a.flags = F_RESET | (d_obs ? F_OBS : 0);
     a.reset_mask = d_reset_mask;
@@ -261,6 +270,7 @@ int agar_set_state(AgarEnv* e, const float* d_src, void* stream) {
     CUDA_OK(cudaSetDevice(e->device));
     CUDA_OK(cudaMemcpyAsync(e->d_state, d_src, (size_t)e->p.c.num_arenas * e->p.L.words * sizeof(float),
                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    e->p.hash_epoch += 1;  // the pellets may have changed: every persisted hash is stale
     return 0;
 }
 

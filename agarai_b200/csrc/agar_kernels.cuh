@@ -31,6 +31,8 @@ struct DevParams {
     int K, KC;
     float hash_inv;   // HASH_W / arena_size: pellet bin index = (int)(coordinate * hash_inv)
     float hash_bs;    // arena_size / HASH_W
+    int hash_epoch;   // persisted hashes carrying another epoch are stale (bumped by agar_set_state / agar_seed)
+    int hash_words;   // words of one arena's persisted hash
     float box_inv;    // 1/box when box is a power of two (then x*box_inv == x/box exactly), else 0
     float raster_lim; // entities farther than this from the centre on either axis cannot land in the grid
     float oob_off[128];  // (float)((double)(i - G/2) * (view/G)), features/extractors.py:87-91
@@ -51,6 +53,7 @@ struct KArgs {
     const uint8_t* reset_mask;  // [N] or null (= all) — only read when F_RESET
     int32_t* events;         // [N,cap,4]
     int32_t* ev_counts;      // [N]
+    int32_t* hash;           // [N, hash_words] persisted pellet hash (null: rebuild every step)
     int32_t flags;
     int32_t n_records;
 };
@@ -154,7 +157,8 @@ __device__ __forceinline__ float hw_treesum(unsigned hmask, float v) {
 // memory as the observation tile, which is only needed after the last tick.
 #define HASH_W 16
 #define HASH_BINS (HASH_W * HASH_W)
-#define EXTRA_CAP 64
+#define EXTRA_CAP 16    // pellets that may respawn before the hash is rebuilt (each is checked by every cell)
+#define HASH_HDR 4      // words of the persisted hash header: {epoch, nextras, 0, 0}
 #define SEG_CAP 256   // bin-row segments queued per tick (overflow is scanned inline)
 
 struct Smem {
@@ -181,10 +185,11 @@ struct Smem {
     uint8_t *oobx, *ooby;                            // [128]
     int32_t* freefood;                               // [F_pad]
     int32_t* rb;                                     // [256] raster: in-view cell entities and patches
-    int32_t* sc;                                     // [16] scalars + [32] list-membership bitmask
+    int32_t* sc;                                     // [32] scalars + [32] list-membership bitmask
 };
 enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT, SC_EVCOUNT, SC_RESET, SC_ALLDONE,
-       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NSEG, SC_NOB };
+       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NSEG, SC_NOB, SC_HBUILT, SC_NEX0, SC_COUNT };
+static_assert(SC_COUNT <= 32, "scalar slots overlap the list-membership bitmask");
 
 __host__ __device__ inline size_t pad4z(size_t n) { return (n + 3) & ~(size_t)3; }
 __host__ __device__ inline size_t scratch_words(const AgarLayout& L) {
@@ -195,6 +200,12 @@ __host__ __device__ inline size_t union_words(const AgarLayout& L, int G) {
     return pad4z(a > t ? a : t);
 }
 __host__ __device__ inline size_t kpad(const AgarLayout& L) { return pad4z((size_t)L.num_players); }
+
+// persisted hash record: the shared-memory block [hstart | sorted | extras] followed by the header
+__host__ __device__ inline size_t hash_body_words(const AgarLayout& L) {
+    return HASH_BINS + 4 + pad4z((size_t)L.P_pad / 2) + EXTRA_CAP / 2;
+}
+__host__ __device__ inline size_t hash_record_words(const AgarLayout& L) { return hash_body_words(L) + HASH_HDR; }
 
 __host__ __device__ inline size_t smem_bytes(const AgarLayout& L, int G) {
     size_t w = 0;
@@ -327,7 +338,7 @@ __device__ void build_hash(const DevParams& p, const Smem& s) {
 #pragma unroll
         for (int q = 0; q < PER; ++q) { s.hstart[lane * PER + q] = run; s.hcur[lane * PER + q] = run; run += c[q]; }
         if (lane == 31) s.hstart[HASH_BINS] = incl;
-        if (lane == 0) { s.sc[SC_NEXTRAS] = 0; s.sc[SC_REBUILD] = 0; s.sc[SC_NHITS] = 0; s.sc[SC_HASHOK] = 1; }
+        if (lane == 0) { s.sc[SC_NEXTRAS] = 0; s.sc[SC_REBUILD] = 0; s.sc[SC_NHITS] = 0; s.sc[SC_HASHOK] = 1; s.sc[SC_HBUILT] = 1; }
     }
     __syncthreads();
     for (int i = tid; i < P; i += nt) {
@@ -672,15 +683,30 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
     float* vx = s.rec + L.virus_x; float* vy = s.rec + L.virus_y;
     float* fx = s.rec + L.food_x; float* fy = s.rec + L.food_y; float* fvx = s.rec + L.food_vx; float* fvy = s.rec + L.food_vy;
     float* grec = a.state + (size_t)arena * L.words;  // write target
-    int32_t* inl = s.sc + 16;                         // bitmask of gids present in the alive list
+    int32_t* inl = s.sc + 32;                         // bitmask of gids present in the alive list (sc[0..31] are scalars)
 
     // ---- stage the record ----
     {
         const float4* src = reinterpret_cast<const float4*>(a.src_state + (size_t)arena * L.words);
         float4* dst = reinterpret_cast<float4*>(s.rec);
-        for (int i = tid; i < L.words / 4; i += nt) dst[i] = __ldg(src + i);
+        for (int i = tid; i < L.words / 4; i += nt) dst[i] = src[i];  // plain loads: the record is rewritten below
         for (int i = tid; i < KC; i += nt) { s.cnt[i] = 0; s.eater[i] = NONE_I; s.gain[i] = 0.0f; }
         if (tid < 64) s.sc[tid] = 0;
+        if (a.flags & F_STEP) {
+            for (int i = tid; i < c.num_pellets; i += nt) s.pwin[i] = NONE_I;
+            for (int i = tid; i < L.P_pad / 32 + 1; i += nt) s.isx[i] = 0;
+        }
+    }
+    // persisted pellet hash of this arena: valid if it carries the handle's current epoch
+    const int4* ghash = a.hash ? reinterpret_cast<const int4*>(a.hash + (size_t)arena * p.hash_words) : nullptr;
+    int4 hhdr = make_int4(0, 0, 0, 0);
+    if ((a.flags & F_STEP) && ghash) {
+        const int body4 = (int)hash_body_words(L) / 4;
+        hhdr = ghash[body4];
+        if (hhdr.x == p.hash_epoch) {
+            int4* dst = reinterpret_cast<int4*>(s.hstart);
+            for (int i = tid; i < body4; i += nt) dst[i] = ghash[i];
+        }
     }
     __syncthreads();
 
@@ -691,8 +717,14 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
 
     if (a.flags & F_STEP) {
         const uint32_t tick0 = (uint32_t)s.reci[L.tick];
-        // ---- pellet hash, alive list ----
-        build_hash(p, s);
+        // ---- pellet hash (persisted across steps, rebuilt when stale), alive list ----
+        if (ghash && hhdr.x == p.hash_epoch) {
+            const int nex = min(hhdr.y, EXTRA_CAP);
+            if (tid < nex) { const int i = s.extras[tid]; atomicOr(&s.isx[i >> 5], 1 << (i & 31)); }
+            if (tid == 0) { s.sc[SC_NEXTRAS] = nex; s.sc[SC_NEX0] = nex; s.sc[SC_HASHOK] = 1; }
+        } else {
+            build_hash(p, s);
+        }
         build_list(p, s);
         for (int base = 0; base < KC; base += nt) {  // membership bits of the list (one word per warp chunk)
             const int g = base + tid;
@@ -772,16 +804,28 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
                 const int bx = hash_coord(p, Cx), by = hash_coord(p, Cy);
                 int x0 = max(bx - 1, 0), x1 = min(bx + 1, HASH_W - 1), y0 = max(by - 1, 0), y1 = min(by + 1, HASH_W - 1);
                 float best = INFINITY; int bi = NONE_I;
+                const int nex = s.sc[SC_NEXTRAS];  // pellets that moved since the hash was built: always examined
                 for (int pass = 0; pass < 2; ++pass) {
                     for (int row = y0; row <= y1; ++row) {
                         const int j1 = s.hstart[row * HASH_W + x1 + 1];
                         for (int j = s.hstart[row * HASH_W + x0] + l4; j < j1; j += 4) {
                             const int i = s.sorted[j];
-                            float dx = px[i] - Cx, dy = py[i] - Cy;
+                            if ((s.isx[i >> 5] >> (i & 31)) & 1) continue;  // stale entry
+                            const float qx = px[i];
+                            if (!(qx >= 0.0f)) continue;
+                            float dx = qx - Cx, dy = py[i] - Cy;
                             if (fabsf(dx) <= R && fabsf(dy) <= R) {
                                 float d2 = dx * dx + dy * dy;
                                 if (d2 < best || (d2 == best && i < bi)) { best = d2; bi = i; }
                             }
+                        }
+                    }
+                    for (int e = l4; e < nex; e += 4) {
+                        const int i = s.extras[e];
+                        float dx = px[i] - Cx, dy = py[i] - Cy;
+                        if (fabsf(dx) <= R && fabsf(dy) <= R) {
+                            float d2 = dx * dx + dy * dy;
+                            if (d2 < best || (d2 == best && i < bi)) { best = d2; bi = i; }
                         }
                     }
 #pragma unroll
@@ -881,7 +925,6 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
             //      cell's (padded) bounding box as segments and checks the few respawned pellets itself ----
             {
                 const int n = s.sc[SC_NLIST];
-                const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
                 for (int q = tid; q < n; q += nt) {
                     const int g = s.list[q];
                     const float m = cm[g];
@@ -919,12 +962,6 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
                                 if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
                         }
                     }
-                    for (int e = 0; e < nex; ++e) {  // respawned since the hash was built
-                        const int i = s.extras[e];
-                        const float ex = px[i] - x, ey = py[i] - y;
-                        if (ex * ex + ey * ey < r2)
-                            if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
-                    }
                 }
                 for (int f = tid; f < F; f += nt)
                     if (fx[f] >= 0.0f) s.sc[SC_FOODANY] = 1;
@@ -947,6 +984,22 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
                         const float ex = qx - x, ey = py[i] - y;
                         if (ex * ex + ey * ey < r2)
                             if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
+                    }
+                }
+                // pellets that respawned since the hash was built: every (cell, pellet) pair, EXTRA_CAP
+                // lanes per cell (a stale hash entry of the same pellet may claim twice: atomicMin dedups)
+                const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
+                if (nex > 0) {
+                    const int n = s.sc[SC_NLIST], e = tid & (EXTRA_CAP - 1);
+                    if (e < nex) {
+                        const int i = s.extras[e];
+                        const float qx = px[i], qy = py[i];
+                        for (int q = tid / EXTRA_CAP; q < n; q += nt / EXTRA_CAP) {
+                            const int g = s.list[q];
+                            const float ex = qx - cx[g], ey = qy - cy[g];
+                            if (ex * ex + ey * ey < cm[g] * r2pm)
+                                if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
+                        }
                     }
                 }
             }
@@ -1199,6 +1252,22 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
             reset_arena(p, s, gid_lo, gid_hi); static_dirty = true;
             if (tid == 0) s.sc[SC_HASHOK] = 0;  // pellets were redrawn: the raster scans them all
         }
+        // ---- persist the pellet hash for the next step ----
+        if (a.hash && !(a.flags & F_READONLY)) {
+            int4* gh = reinterpret_cast<int4*>(a.hash + (size_t)arena * p.hash_words);
+            const int body4 = (int)hash_body_words(L) / 4, ex4 = (HASH_BINS + 4 + (int)pad4z((size_t)L.P_pad / 2)) / 4;
+            const int4* src = reinterpret_cast<const int4*>(s.hstart);
+            const bool ok = s.sc[SC_HASHOK] != 0;
+            const int nexn = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
+            if (ok && s.sc[SC_HBUILT]) {                   // rebuilt this step: bins + order + respawn list
+                for (int i = tid; i < body4; i += nt) gh[i] = src[i];
+            } else if (ok && nexn != s.sc[SC_NEX0]) {      // only the respawn list grew
+                for (int i = ex4 + tid; i < body4; i += nt) gh[i] = src[i];
+            }
+            const bool stale = !ok || s.sc[SC_REBUILD] != 0;  // redrawn pellets / overflowed list: rebuild next step
+            if (tid == 0 && (stale || s.sc[SC_HBUILT] || nexn != s.sc[SC_NEX0] || hhdr.x != p.hash_epoch))
+                gh[body4] = make_int4(stale ? 0 : p.hash_epoch, nexn, 0, 0);
+        }
         if (c.event_capacity > 0 && tid == 0) a.ev_counts[arena] = s.sc[SC_EVCOUNT];
     }
 
@@ -1213,7 +1282,7 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
     if ((a.flags & F_OBS) && a.obs) {
         __syncthreads();  // the tile shares memory with the pellet hash
         const int GG = c.grid_size * c.grid_size;
-        raster_arena(p, s, a.obs + (size_t)arena * A * p.C * GG, s.sc[SC_HASHOK] != 0);
+        raster_arena(p, s, a.obs + (size_t)arena * A * p.C * GG, s.sc[SC_HASHOK] != 0 && s.sc[SC_REBUILD] == 0);
     }
 }
 
