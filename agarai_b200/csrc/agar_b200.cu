@@ -43,6 +43,7 @@ struct AgarEnv {
     int32_t* d_tab_act = nullptr;
     int32_t n_actions = 0;
     size_t smem = 0;
+    int min_blocks = 5;  // which agar_step_kernel instantiation to launch
     int64_t launches = 0;
     // staging for agar_step_host
     float* d_target = nullptr; int32_t* d_act = nullptr; float* d_obs = nullptr;
@@ -59,7 +60,11 @@ size_t obs_elems(const AgarEnv* e) {
 
 int launch(AgarEnv* e, KArgs& a, int n_records, cudaStream_t st) {
     a.n_records = n_records;
-    agar_step_kernel<kThreads><<<n_records, kThreads, e->smem, st>>>(e->p, a);
+    switch (e->min_blocks) {
+        case 7: agar_step_kernel<kThreads, 7><<<n_records, kThreads, e->smem, st>>>(e->p, a); break;
+        case 6: agar_step_kernel<kThreads, 6><<<n_records, kThreads, e->smem, st>>>(e->p, a); break;
+        default: agar_step_kernel<kThreads, 5><<<n_records, kThreads, e->smem, st>>>(e->p, a); break;
+    }
     CUDA_OK(cudaGetLastError());
     e->launches += 1;
     return 0;
@@ -135,7 +140,12 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
         delete e;
         return fail("arena record + observation tile do not fit in shared memory (" + std::to_string(e->smem) + " B)");
     }
-    CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    // CTAs per SM that the shared memory allows (1 KB per CTA is reserved by the system)
+    const int fit = (int)((size_t)prop.sharedMemPerMultiprocessor / (e->smem + 1024));
+    e->min_blocks = fit >= 7 ? 7 : (fit == 6 ? 6 : 5);
+    CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     const size_t state_bytes = (size_t)cfg->num_arenas * p.L.words * sizeof(float);
     CUDA_OK(cudaMalloc(&e->d_state, state_bytes));
     CUDA_OK(cudaMemset(e->d_state, 0, state_bytes));

@@ -86,6 +86,38 @@ __device__ __forceinline__ void rand_pos(const DevParams& p, uint32_t gid_lo, ui
 
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// ------------------------------------------------------------- TMA bulk copies (1-D) + mbarrier
+// The arena record and its persisted pellet hash are contiguous blocks of global memory: one thread
+// issues `cp.async.bulk` (UBLKCP) into shared memory, completion is counted in bytes on an mbarrier,
+// and the whole CTA waits on its phase.  The rewritten part of the record goes back the same way.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // ------------------------------------------------------------- half-warp (one player) helpers
 // A player's 16 cell slots map to the 16 lanes of a half-warp: hmask names that half, hbase is
 // 0 or 16, slot = lane & 15.  Every lane of the half must call these together.
@@ -168,6 +200,8 @@ struct Smem {
     int32_t* hstart;  // [HASH_BINS+1] first sorted position of each bin
     uint16_t* sorted; // [P_pad]       pellet ids in bin order
     uint16_t* extras; // [EXTRA_CAP]   pellets respawned since the hash was built (unique)
+    int32_t* hhdr;    // [HASH_HDR]    header of the persisted hash record: {epoch, nextras, 0, 0}
+    uint64_t* mbar;   // mbarrier for the bulk copies (2 words)
     int32_t* isx;     // [P_pad/32+1]  bit per pellet: respawned since the hash was built
     // union: the observation tile (only needed after the last tick) over the per-tick scratch
     float* tile;      // [G*G] one observation channel
@@ -210,7 +244,7 @@ __host__ __device__ inline size_t hash_record_words(const AgarLayout& L) { retur
 __host__ __device__ inline size_t smem_bytes(const AgarLayout& L, int G) {
     size_t w = 0;
     w += (size_t)L.words;                                   // rec
-    w += HASH_BINS + 4 + pad4z((size_t)L.P_pad / 2) + EXTRA_CAP / 2 + pad4z((size_t)L.P_pad / 32 + 1);  // hash kept
+    w += HASH_BINS + 4 + pad4z((size_t)L.P_pad / 2) + EXTRA_CAP / 2 + HASH_HDR + 4 + pad4z((size_t)L.P_pad / 32 + 1);  // hash kept, header, mbarrier
     w += union_words(L, G);                                 // tile | scratch
     w += (size_t)(L.V_pad + 4);                             // vwin
     w += kpad(L) * 10;                                      // per-player arrays
@@ -228,6 +262,8 @@ __device__ __forceinline__ Smem carve(float* base, const AgarLayout& L, int G) {
     s.hstart = (int32_t*)p; p += HASH_BINS + 4;
     s.sorted = (uint16_t*)p; p += pad4z((size_t)L.P_pad / 2);
     s.extras = (uint16_t*)p; p += EXTRA_CAP / 2;
+    s.hhdr = (int32_t*)p; p += HASH_HDR;                     // contiguous with the body: one bulk copy
+    s.mbar = (uint64_t*)p; p += 4;
     s.isx = (int32_t*)p; p += pad4z((size_t)L.P_pad / 32 + 1);
     s.tile = p;
     {
@@ -662,8 +698,10 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
 //              apply gains + virus claims | B | [pops] | cell-eats-cell test | B | [apply] |
 //              merge (half-warp per player, shuffles) | B
 //   rewards/dones | B | write back | raster.
-template <int kThreads>
-__global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_constant__ DevParams p,
+// kMinBlocks is chosen by the host from the shared-memory footprint (CTAs that fit per SM) so that the
+// register budget never becomes the occupancy limit: 5 -> <=100 regs, 6 -> <=80, 7 -> <=72.
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const __grid_constant__ DevParams p,
                                                                const __grid_constant__ KArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
     const AgarLayout& L = p.L;
@@ -685,11 +723,18 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
     float* grec = a.state + (size_t)arena * L.words;  // write target
     int32_t* inl = s.sc + 32;                         // bitmask of gids present in the alive list (sc[0..31] are scalars)
 
-    // ---- stage the record ----
-    {
-        const float4* src = reinterpret_cast<const float4*>(a.src_state + (size_t)arena * L.words);
-        float4* dst = reinterpret_cast<float4*>(s.rec);
-        for (int i = tid; i < L.words / 4; i += nt) dst[i] = src[i];  // plain loads: the record is rewritten below
+    // ---- stage the record (and the persisted pellet hash) with TMA bulk copies ----
+    int32_t* ghash = a.hash ? a.hash + (size_t)arena * p.hash_words : nullptr;
+    const bool load_hash = (a.flags & F_STEP) && ghash;
+    if (tid == 0) mbar_init(s.mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t rec_bytes = (uint32_t)L.words * 4u, hash_bytes = load_hash ? (uint32_t)p.hash_words * 4u : 0u;
+        mbar_expect_tx(s.mbar, rec_bytes + hash_bytes);
+        bulk_g2s(s.rec, a.src_state + (size_t)arena * L.words, rec_bytes, s.mbar);
+        if (load_hash) bulk_g2s(s.hstart, ghash, hash_bytes, s.mbar);
+    }
+    {   // meanwhile: clear the per-tick scratch
         for (int i = tid; i < KC; i += nt) { s.cnt[i] = 0; s.eater[i] = NONE_I; s.gain[i] = 0.0f; }
         if (tid < 64) s.sc[tid] = 0;
         if (a.flags & F_STEP) {
@@ -697,18 +742,11 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
             for (int i = tid; i < L.P_pad / 32 + 1; i += nt) s.isx[i] = 0;
         }
     }
-    // persisted pellet hash of this arena: valid if it carries the handle's current epoch
-    const int4* ghash = a.hash ? reinterpret_cast<const int4*>(a.hash + (size_t)arena * p.hash_words) : nullptr;
-    int4 hhdr = make_int4(0, 0, 0, 0);
-    if ((a.flags & F_STEP) && ghash) {
-        const int body4 = (int)hash_body_words(L) / 4;
-        hhdr = ghash[body4];
-        if (hhdr.x == p.hash_epoch) {
-            int4* dst = reinterpret_cast<int4*>(s.hstart);
-            for (int i = tid; i < body4; i += nt) dst[i] = ghash[i];
-        }
-    }
+    mbar_wait(s.mbar, 0);
     __syncthreads();
+    // persisted pellet hash of this arena: valid if it carries the handle's current epoch
+    int4 hhdr = make_int4(0, 0, 0, 0);
+    if (load_hash) hhdr = *reinterpret_cast<const int4*>(s.hhdr);
 
     bool static_dirty = false;  // whole record must be written back (after a reset)
     if (a.flags & F_RESET) {
@@ -718,7 +756,7 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
     if (a.flags & F_STEP) {
         const uint32_t tick0 = (uint32_t)s.reci[L.tick];
         // ---- pellet hash (persisted across steps, rebuilt when stale), alive list ----
-        if (ghash && hhdr.x == p.hash_epoch) {
+        if (load_hash && hhdr.x == p.hash_epoch) {
             const int nex = min(hhdr.y, EXTRA_CAP);
             if (tid < nex) { const int i = s.extras[tid]; atomicOr(&s.isx[i >> 5], 1 << (i & 31)); }
             if (tid == 0) { s.sc[SC_NEXTRAS] = nex; s.sc[SC_NEX0] = nex; s.sc[SC_HASHOK] = 1; }
@@ -1271,12 +1309,15 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
         if (c.event_capacity > 0 && tid == 0) a.ev_counts[arena] = s.sc[SC_EVCOUNT];
     }
 
-    // ---- write back ----
+    // ---- write back: one bulk store of the rewritten part (the whole record after a reset) ----
     if (!(a.flags & F_READONLY) && (a.flags & (F_STEP | F_RESET))) {
         const int w0 = static_dirty ? 0 : L.dyn_begin;  // dyn_begin % 4 == 0
-        const float4* src = reinterpret_cast<const float4*>(s.rec);
-        float4* dst = reinterpret_cast<float4*>(grec);
-        for (int i = w0 / 4 + tid; i < L.words / 4; i += nt) dst[i] = src[i];
+        __syncthreads();                 // every thread's writes to the record are done
+        if (tid == 0) {
+            fence_async_all();           // ... and ordered before the async proxy (shared and global)
+            bulk_s2g(grec + w0, s.rec + w0, (uint32_t)(L.words - w0) * 4u);
+            bulk_commit();
+        }
     }
     // ---- observations ----
     if ((a.flags & F_OBS) && a.obs) {
@@ -1284,6 +1325,7 @@ __global__ void __launch_bounds__(kThreads, 4) agar_step_kernel(const __grid_con
         const int GG = c.grid_size * c.grid_size;
         raster_arena(p, s, a.obs + (size_t)arena * A * p.C * GG, s.sc[SC_HASHOK] != 0 && s.sc[SC_REBUILD] == 0);
     }
+    if (tid == 0) bulk_wait_read0();  // the bulk store must have read the record before the CTA exits
 }
 
 // -------------------------------------------------------------------------------- GAE
