@@ -959,11 +959,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         for (int tk = 0; tk < c.ticks_per_step; ++tk) {
             const uint32_t tick = tick0 + (uint32_t)tk;
             if (s.sc[SC_REBUILD]) build_hash(p, s);  // too many respawns since the last build (uniform)
-            // ---- motion: one thread per alive cell; it queues the runs of the pellet hash under the
-            //      cell's (padded) bounding box as segments and checks the few respawned pellets itself ----
+            // ---- motion + pellet query: four lanes per alive cell.  All four evaluate the motion (lane 0
+            //      stores it) and then share the scan of the hash runs under the cell's padded bounding
+            //      box and of the respawn list.  A pellet whose centre lies inside the disc is claimed
+            //      with atomicMin: the lowest gid wins ----
             {
                 const int n = s.sc[SC_NLIST];
-                for (int q = tid; q < n; q += nt) {
+                const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
+                const int l4 = lane & 3;
+                for (int q = tid >> 2; q < n; q += nt >> 2) {
                     const int g = s.list[q];
                     const float m = cm[g];
                     if (!(m > 0.0f)) continue;  // died earlier in this step
@@ -971,27 +975,27 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     const float r2 = m * r2pm;
                     const float r = sqrtf(r2);
                     float spd = c.speed_k / sqrtf(r);
-                    float dx = s.Tx[k] - cx[g], dy = s.Ty[k] - cy[g];
+                    const float ox = cx[g], oy = cy[g], oix = cix[g], oiy = ciy[g], t = ct[g];
+                    float dx = s.Tx[k] - ox, dy = s.Ty[k] - oy;
                     float d = sqrtf(dx * dx + dy * dy);
                     float den = d > c.target_reach ? d : c.target_reach;
                     float sc = spd / den;
-                    float nx = cx[g] + (dx * sc + cix[g]);
-                    float ny = cy[g] + (dy * sc + ciy[g]);
-                    float ix = cix[g] * c.impulse_decay, iy = ciy[g] * c.impulse_decay;
+                    float nx = ox + (dx * sc + oix);
+                    float ny = oy + (dy * sc + oiy);
+                    float ix = oix * c.impulse_decay, iy = oiy * c.impulse_decay;
                     if (fabsf(ix) < 1e-3f && fabsf(iy) < 1e-3f) { ix = 0.0f; iy = 0.0f; }
                     const float x = clampf(nx, 0.0f, arena_size), y = clampf(ny, 0.0f, arena_size);
-                    cx[g] = x; cy[g] = y; cix[g] = ix; ciy[g] = iy;
-                    float t = ct[g];
-                    if (t > 0.0f) ct[g] = t - 1.0f;
+                    __syncwarp(0xFu << (lane & ~3));  // the quad has read the old state
+                    if (l4 == 0) {
+                        cx[g] = x; cy[g] = y; cix[g] = ix; ciy[g] = iy;
+                        if (t > 0.0f) ct[g] = t - 1.0f;
+                    }
                     const float rp = r * 1.001f + 0.01f;
                     const int bx0 = hash_coord(p, x - rp), bx1 = hash_coord(p, x + rp);
                     const int by0 = hash_coord(p, y - rp), by1 = hash_coord(p, y + rp);
                     for (int by = by0; by <= by1; ++by) {
-                        const int j0 = s.hstart[by * HASH_W + bx0], j1 = s.hstart[by * HASH_W + bx1 + 1];
-                        if (j1 <= j0) continue;
-                        const int si = atomicAdd(&s.sc[SC_NSEG], 1);
-                        if (si < SEG_CAP) { s.seg[si] = make_int2(g, j0 | (j1 << 16)); continue; }
-                        for (int j = j0; j < j1; ++j) {  // work list full: scan the run here
+                        const int j1 = s.hstart[by * HASH_W + bx1 + 1];
+                        for (int j = s.hstart[by * HASH_W + bx0] + l4; j < j1; j += 4) {
                             const int i = s.sorted[j];
                             const float qx = px[i];
                             if (!(qx >= 0.0f)) continue;
@@ -1000,51 +1004,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                                 if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
                         }
                     }
+                    for (int e = l4; e < nex; e += 4) {  // respawned since the hash was built (a stale hash
+                        const int i = s.extras[e];       // entry of the same pellet may claim twice: atomicMin dedups)
+                        const float ex = px[i] - x, ey = py[i] - y;
+                        if (ex * ex + ey * ey < r2)
+                            if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
+                    }
                 }
                 for (int f = tid; f < F; f += nt)
                     if (fx[f] >= 0.0f) s.sc[SC_FOODANY] = 1;
                 for (int v = tid; v < V; v += nt) s.vwin[v] = NONE_I;
             }
             __syncthreads();
-            // ---- pellet query: groups of 8 lanes scan the queued segments; a pellet whose centre lies
-            //      inside the disc is claimed with atomicMin (lowest gid wins) ----
-            {
-                const int nseg = min(s.sc[SC_NSEG], SEG_CAP);
-                const int l8 = tid & 7;
-                for (int sgi = tid >> 3; sgi < nseg; sgi += nt >> 3) {
-                    const int2 sg = s.seg[sgi];
-                    const int g = sg.x, j1 = (int)((unsigned)sg.y >> 16);
-                    const float x = cx[g], y = cy[g], r2 = cm[g] * r2pm;
-                    for (int j = (sg.y & 0xFFFF) + l8; j < j1; j += 8) {
-                        const int i = s.sorted[j];
-                        const float qx = px[i];
-                        if (!(qx >= 0.0f)) continue;
-                        const float ex = qx - x, ey = py[i] - y;
-                        if (ex * ex + ey * ey < r2)
-                            if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
-                    }
-                }
-                // pellets that respawned since the hash was built: every (cell, pellet) pair, EXTRA_CAP
-                // lanes per cell (a stale hash entry of the same pellet may claim twice: atomicMin dedups)
-                const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
-                if (nex > 0) {
-                    const int n = s.sc[SC_NLIST], e = tid & (EXTRA_CAP - 1);
-                    if (e < nex) {
-                        const int i = s.extras[e];
-                        const float qx = px[i], qy = py[i];
-                        for (int q = tid / EXTRA_CAP; q < n; q += nt / EXTRA_CAP) {
-                            const int g = s.list[q];
-                            const float ex = qx - cx[g], ey = qy - cy[g];
-                            if (ex * ex + ey * ey < cm[g] * r2pm)
-                                if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
+            const int nh = s.sc[SC_NHITS];                // block-uniform from here on
+            const bool food_any = s.sc[SC_FOODANY] != 0;
+            const bool gains = nh > 0 || food_any;        // some mass changes this tick before the eat test
             // ---- resolve the claimed pellets: winner = lowest gid (atomicMin), respawn by Philox ----
-            {
-                const int nh = s.sc[SC_NHITS];
+            if (nh > 0) {
                 for (int h = tid; h < nh; h += nt) {
                     const int i = s.hits[h];
                     const int g = s.pwin[i];
@@ -1062,9 +1038,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     px[i] = nx; py[i] = ny;
                     if (!(a.flags & F_READONLY)) { grec[L.pellet_x + i] = nx; grec[L.pellet_y + i] = ny; }
                 }
+                __syncthreads();
             }
-            __syncthreads();
-            const bool food_any = s.sc[SC_FOODANY] != 0;  // block-uniform
             if (food_any) {
                 // ---- pellet gains, then foods: move, eaten by the lowest-gid cell holding the centre ----
                 const int n = s.sc[SC_NLIST];
@@ -1097,8 +1072,36 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 }
                 __syncthreads();
             }
-            // ---- apply gains (pellets, or foods when present); heavy cells claim viruses ----
-            {
+            // cell-eats-cell test (different players, pre-phase snapshot): four lanes per prey, each
+            // scanning a quarter of the possible eaters; the lowest gid wins
+            auto eat_test = [&]() {
+                const int n = s.sc[SC_NLIST];
+                const unsigned qmask = 0xFu << (lane & ~3);
+                const int l4 = lane & 3;
+                for (int q = tid >> 2; q < n; q += nt >> 2) {
+                    const int j = s.list[q];
+                    const float mj = cm[j];
+                    const float need = mj * c.eat_ratio, x = cx[j], y = cy[j];
+                    const int kj = j >> 4;
+                    int best = NONE_I;
+                    if (mj > 0.0f) {
+#pragma unroll 4
+                        for (int qi = l4; qi < n; qi += 4) {
+                            const int i = s.list[qi];
+                            const float mi = cm[i];
+                            if ((i >> 4) == kj || !(mi >= need)) continue;  // need > 0, so dead cells fail here
+                            const float dx = x - cx[i], dy = y - cy[i];
+                            if (dx * dx + dy * dy < mi * r2pm && i < best) best = i;
+                        }
+                    }
+                    best = min(best, __shfl_xor_sync(qmask, best, 1));
+                    best = min(best, __shfl_xor_sync(qmask, best, 2));
+                    if (l4 == 0 && best != NONE_I) { s.eater[j] = best; s.sc[SC_ANYEAT] = 1; }
+                }
+            };
+            // ---- apply gains (pellets, or foods when present); heavy cells claim viruses.  On a tick
+            //      without gains no mass changes here, so the eat test runs in the same phase ----
+            if (gains || V > 0) {
                 const int n = s.sc[SC_NLIST];
                 const float unit = food_any ? c.food_mass : c.pellet_mass;
                 for (int q = tid; q < n; q += nt) {
@@ -1114,17 +1117,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                         }
                     }
                 }
-                if (tid == 0) { s.sc[SC_NHITS] = 0; s.sc[SC_FOODANY] = 0; s.sc[SC_NSEG] = 0; }
             }
-            __syncthreads();
+            if (tid == 0 && gains) { s.sc[SC_NHITS] = 0; s.sc[SC_FOODANY] = 0; }  // a barrier follows whenever gains
+            if (K > 1 && !gains) eat_test();
+            if (gains || V > 0 || K > 1) __syncthreads();
+            bool eat_done = K > 1 && !gains;
             // ---- virus pops ----
-            if (s.sc[SC_ANYVHIT]) {  // block-uniform, rare
+            if (V > 0 && s.sc[SC_ANYVHIT]) {  // block-uniform, rare
                 const int n = s.sc[SC_NLIST];
                 for (int q = tid; q < n; q += nt) {
                     const int g = s.list[q];
+                    if (eat_done) s.eater[g] = NONE_I;  // the speculative eat test is void: masses change below
                     if (!(cm[g] >= c.virus_pop_mass)) continue;
                     for (int v = 0; v < V; ++v)
-                        if (s.vwin[v] == g) { s.eater[g] = v; break; }
+                        if (s.vwin[v] == g) { s.eater[g] = v; break; }   // eater[] doubles as "first virus won"
                 }
                 __syncthreads();
                 // one thread per player walks its slots in order (free slots are consumed sequentially
@@ -1164,37 +1170,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                         if (!(a.flags & F_READONLY)) { grec[L.virus_x + v] = nx; grec[L.virus_y + v] = ny; }
                     }
                 }
+                if (tid == 0) { s.sc[SC_ANYVHIT] = 0; s.sc[SC_ANYEAT] = 0; }
+                eat_done = false;
                 __syncthreads();
-                if (tid == 0) s.sc[SC_ANYVHIT] = 0;
             }
-            // ---- cell eats cell (different players) on the pre-phase snapshot ----
+            // ---- cell eats cell ----
             if (K > 1) {
-                // four lanes per prey, each scanning a quarter of the possible eaters; lowest gid wins
-                const int n = s.sc[SC_NLIST];
-                const unsigned qmask = 0xFu << (lane & ~3);
-                const int l4 = lane & 3;
-                for (int q = tid >> 2; q < n; q += nt >> 2) {
-                    const int j = s.list[q];
-                    const float mj = cm[j];
-                    const float need = mj * c.eat_ratio, x = cx[j], y = cy[j];
-                    const int kj = j >> 4;
-                    int best = NONE_I;
-                    if (mj > 0.0f) {
-#pragma unroll 4
-                        for (int qi = l4; qi < n; qi += 4) {
-                            const int i = s.list[qi];
-                            const float mi = cm[i];
-                            if ((i >> 4) == kj || !(mi >= need)) continue;  // need > 0, so dead cells fail here
-                            const float dx = x - cx[i], dy = y - cy[i];
-                            if (dx * dx + dy * dy < mi * r2pm && i < best) best = i;
-                        }
-                    }
-                    best = min(best, __shfl_xor_sync(qmask, best, 1));
-                    best = min(best, __shfl_xor_sync(qmask, best, 2));
-                    if (l4 == 0 && best != NONE_I) { s.eater[j] = best; s.sc[SC_ANYEAT] = 1; }
-                }
-                __syncthreads();
+                if (!eat_done) { eat_test(); __syncthreads(); }
                 if (s.sc[SC_ANYEAT]) {
+                    const int n = s.sc[SC_NLIST];
                     if (tid < 32) {  // gains added in ascending prey order (float sum order is part of the spec)
                         for (int base = 0; base < KC; base += 32) {
                             int j = base + lane;
@@ -1258,8 +1242,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                         cm[g] = acc;
                     }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
 
         // ---- rewards / dones ----
