@@ -19,6 +19,7 @@
 
 #define MC AGAR_MAX_CELLS
 #define NONE_I 0x7fffffff
+#define NONE16 0xFFFFu
 
 namespace agar {
 
@@ -85,6 +86,18 @@ __device__ __forceinline__ void rand_pos(const DevParams& p, uint32_t gid_lo, ui
 }
 
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// 16-bit atomic min (compare-and-swap loop; claims are rare so it almost never iterates).
+// Returns true for the thread that replaced NONE16, i.e. the first claimer of the slot.
+__device__ __forceinline__ bool claim_min16(uint16_t* addr, int g) {
+    unsigned short old = *reinterpret_cast<volatile unsigned short*>(addr);
+    while ((unsigned)g < (unsigned)old) {
+        const unsigned short prev = atomicCAS(reinterpret_cast<unsigned short*>(addr), old, (unsigned short)g);
+        if (prev == old) return old == NONE16;
+        old = prev;
+    }
+    return false;
+}
 
 // ------------------------------------------------------------- TMA bulk copies (1-D) + mbarrier
 // The arena record and its persisted pellet hash are contiguous blocks of global memory: one thread
@@ -191,7 +204,6 @@ __device__ __forceinline__ float hw_treesum(unsigned hmask, float v) {
 #define HASH_BINS (HASH_W * HASH_W)
 #define EXTRA_CAP 16    // pellets that may respawn before the hash is rebuilt (each is checked by every cell)
 #define HASH_HDR 4      // words of the persisted hash header: {epoch, nextras, 0, 0}
-#define SEG_CAP 256   // bin-row segments queued per tick (overflow is scanned inline)
 
 struct Smem {
     float* rec;       // [words] the arena record
@@ -204,10 +216,9 @@ struct Smem {
     uint64_t* mbar;   // mbarrier for the bulk copies (2 words)
     int32_t* isx;     // [P_pad/32+1]  bit per pellet: respawned since the hash was built
     // union: the observation tile (only needed after the last tick) over the per-tick scratch
-    float* tile;      // [G*G] one observation channel
+    uint32_t* tile;   // [G*G/2] one count channel, two 16-bit bins per word (exact integer atomics)
     int32_t* hcur;    // [HASH_BINS]   counting-sort cursors (only while the hash is built)
-    int2* seg;        // [SEG_CAP]     per-tick work list: (cell gid, j0 | j1 << 16) runs of `sorted` to scan; same memory as hcur
-    int32_t* pwin;    // [P_pad]       winner cell of each pellet this tick (atomicMin)
+    uint16_t* pwin;   // [P_pad]       winner cell of each pellet this tick (16-bit CAS-min), NONE16 = unclaimed
     uint16_t* hits;   // [P_pad]       pellets claimed this tick (bin cache while the hash is built)
     int32_t* list;    // [KC] gids of the alive cells (unordered)
     int32_t* cnt;     // [KC] pellets / foods eaten this tick
@@ -222,15 +233,15 @@ struct Smem {
     int32_t* sc;                                     // [32] scalars + [32] list-membership bitmask
 };
 enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT, SC_EVCOUNT, SC_RESET, SC_ALLDONE,
-       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NSEG, SC_NOB, SC_HBUILT, SC_NEX0, SC_COUNT };
+       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NOB, SC_HBUILT, SC_NEX0, SC_COUNT };
 static_assert(SC_COUNT <= 32, "scalar slots overlap the list-membership bitmask");
 
 __host__ __device__ inline size_t pad4z(size_t n) { return (n + 3) & ~(size_t)3; }
 __host__ __device__ inline size_t scratch_words(const AgarLayout& L) {
-    return 2 * SEG_CAP + (size_t)L.P_pad + (size_t)L.P_pad / 2 + (size_t)L.cells_total * 4;  // 2*SEG_CAP >= HASH_BINS
+    return HASH_BINS + (size_t)L.P_pad / 2 + (size_t)L.P_pad / 2 + (size_t)L.cells_total * 4;
 }
 __host__ __device__ inline size_t union_words(const AgarLayout& L, int G) {
-    size_t a = scratch_words(L), t = (size_t)G * G;
+    size_t a = scratch_words(L), t = (size_t)G * G / 2;
     return pad4z(a > t ? a : t);
 }
 __host__ __device__ inline size_t kpad(const AgarLayout& L) { return pad4z((size_t)L.num_players); }
@@ -265,11 +276,11 @@ __device__ __forceinline__ Smem carve(float* base, const AgarLayout& L, int G) {
     s.hhdr = (int32_t*)p; p += HASH_HDR;                     // contiguous with the body: one bulk copy
     s.mbar = (uint64_t*)p; p += 4;
     s.isx = (int32_t*)p; p += pad4z((size_t)L.P_pad / 32 + 1);
-    s.tile = p;
+    s.tile = (uint32_t*)p;
     {
         int32_t* h = (int32_t*)p;
-        s.hcur = h; s.seg = (int2*)h; h += 2 * SEG_CAP;
-        s.pwin = h; h += L.P_pad;
+        s.hcur = h; h += HASH_BINS;
+        s.pwin = (uint16_t*)h; h += L.P_pad / 2;
         s.hits = (uint16_t*)h; h += L.P_pad / 2;
         s.list = h; h += L.cells_total;
         s.cnt = h; h += L.cells_total;
@@ -353,7 +364,7 @@ __device__ void build_hash(const DevParams& p, const Smem& s) {
     __syncthreads();
     for (int i = tid; i < P; i += nt) {
         const float x = px[i];
-        s.pwin[i] = NONE_I;
+        s.pwin[i] = NONE16;
         int b = 0xFFFF;
         if (x >= 0.0f) { b = hash_coord(p, py[i]) * HASH_W + hash_coord(p, x); atomicAdd(&s.hcur[b], 1); }
         s.hits[i] = (uint16_t)b;  // bin cache for the scatter pass
@@ -405,6 +416,12 @@ __device__ __forceinline__ void build_list(const DevParams& p, const Smem& s) {
             if (al) s.list[pos + __popc(b & ((1u << lane) - 1u))] = g;
         }
     }
+}
+
+// count one entity in a bin of the packed 16-bit tile
+__device__ __forceinline__ void tile_inc(uint32_t* tile, int bin) { atomicAdd(&tile[bin >> 1], (bin & 1) ? 0x10000u : 1u); }
+__device__ __forceinline__ float4 tile_unpack(uint2 w) {
+    return make_float4((float)(w.x & 0xFFFFu), (float)(w.x >> 16), (float)(w.y & 0xFFFFu), (float)(w.y >> 16));
 }
 
 // features/extractors.py:77-78: grid index of an offset, int() truncation toward zero
@@ -461,8 +478,8 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
 
     // the tile shares its memory with the per-tick scratch: clear it first
     {
-        float4* t4 = reinterpret_cast<float4*>(s.tile);
-        for (int i = tid; i < GG / 4; i += nt) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint4* t4 = reinterpret_cast<uint4*>(s.tile);  // GG/2 words, GG % 16 == 0
+        for (int i = tid; i < GG / 8; i += nt) t4[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     // centroids of all agents (half-warp per agent)
     for (int g = tid; g < A * MC; g += nt) {
@@ -503,7 +520,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
         }
         __syncthreads();
         const int nob = s.sc[SC_NOB];
-        const bool others_tile = nob > 32;  // more cells in view than one warp holds: use the tile path
+        const bool others_tile = nob > 32;  // more cells in view than one warp holds: sequential patch path
         // ---- warp 0: ordered sums for the own-cells and others channels -> patch lists ----
         if (tid < 32) {
             pt_bin[lane] = -1; pt_bin[32 + lane] = -1;
@@ -545,7 +562,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
             const bool mass = flag == AGAR_OBS_CELLS || flag == AGAR_OBS_OTHERS;
             if (flag == AGAR_OBS_CELLS) ch_cells = ch;
             if (flag == AGAR_OBS_OTHERS) ch_others = ch;
-            const bool via_tile = !mass || (flag == AGAR_OBS_OTHERS && others_tile);
+            const bool via_tile = !mass;
             if (via_tile && has) {
                 if (flag == AGAR_OBS_PELLETS && use_hash) {
                     // pellets under the view window: hash rows (one warp per row), skipping entries that
@@ -562,7 +579,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                             const float dx = x - cx, dy = py[i] - cy;
                             if (fabsf(dx) > lim || fabsf(dy) > lim) continue;
                             const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
-                            if (0 <= gx && gx < G && 0 <= gy && gy < G) atomicAdd(&s.tile[gx * G + gy], 1.0f);
+                            if (0 <= gx && gx < G && 0 <= gy && gy < G) tile_inc(s.tile, gx * G + gy);
                         }
                     }
                     const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
@@ -571,7 +588,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                         const float dx = px[i] - cx, dy = py[i] - cy;
                         if (fabsf(dx) > lim || fabsf(dy) > lim) continue;
                         const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
-                        if (0 <= gx && gx < G && 0 <= gy && gy < G) atomicAdd(&s.tile[gx * G + gy], 1.0f);
+                        if (0 <= gx && gx < G && 0 <= gy && gy < G) tile_inc(s.tile, gx * G + gy);
                     }
                 } else if (!mass) {
                     // point entities: value 1 each (add_ones with len(entity) <= 2); float adds of 1.0
@@ -586,49 +603,29 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                         float dx = x - cx, dy = y - cy;
                         if (fabsf(dx) > lim || fabsf(dy) > lim) continue;  // cannot land in the grid
                         int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
-                        if (0 <= gx && gx < G && 0 <= gy && gy < G) atomicAdd(&s.tile[gx * G + gy], 1.0f);
-                    }
-                } else if (tid < 32) {
-                    // others, crowded view: masses accumulated strictly in (player, slot) order by warp 0
-                    for (int base = 0; base < p.KC; base += 32) {
-                        int g = base + lane;
-                        float m = (g < p.KC) ? cm[g] : 0.0f;
-                        int bin = -1;
-                        if (m > 0.0f && (g >> 4) != a) {
-                            float dx = cxs[g] - cx, dy = cys[g] - cy;
-                            if (!(fabsf(dx) > lim || fabsf(dy) > lim)) {
-                                int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
-                                if (0 <= gx && gx < G && 0 <= gy && gy < G) bin = gx * G + gy;
-                            }
-                        }
-                        unsigned mask = __ballot_sync(0xffffffffu, bin >= 0);
-                        while (mask) {
-                            int src = __ffs(mask) - 1;
-                            if (lane == src) s.tile[bin] = s.tile[bin] + m;
-                            __syncwarp();
-                            mask &= mask - 1;
-                        }
+                        if (0 <= gx && gx < G && 0 <= gy && gy < G) tile_inc(s.tile, gx * G + gy);
                     }
                 }
             }
             if (via_tile) {
                 __syncthreads();
                 // write the channel out with 128-bit streaming stores and re-zero the tile
-                float4* tile4 = reinterpret_cast<float4*>(s.tile);
+                uint2* tile2 = reinterpret_cast<uint2*>(s.tile);
+                const uint2 zero2 = make_uint2(0u, 0u);
                 if (!sentinel) {
-                    for (int i = tid; i < GG / 4; i += nt) { __stcs(out4 + i, tile4[i]); tile4[i] = zero4; }
+                    for (int i = tid; i < GG / 4; i += nt) { __stcs(out4 + i, tile_unpack(tile2[i])); tile2[i] = zero2; }
                 } else if (fast) {
                     const bool o0 = s.ooby[gy_t], o1 = s.ooby[gy_t + 1], o2 = s.ooby[gy_t + 2], o3 = s.ooby[gy_t + 3];
                     for (int i = tid, gx = gx_t; i < GG / 4; i += nt, gx += rstep) {
-                        float4 v = tile4[i];
+                        float4 v = tile_unpack(tile2[i]);
                         if (s.oobx[gx]) v = neg4;
                         else { if (o0) v.x = -1.0f; if (o1) v.y = -1.0f; if (o2) v.z = -1.0f; if (o3) v.w = -1.0f; }
                         __stcs(out4 + i, v);
-                        tile4[i] = zero4;
+                        tile2[i] = zero2;
                     }
                 } else {
                     for (int i = tid; i < GG / 4; i += nt) {
-                        float4 v = tile4[i];
+                        float4 v = tile_unpack(tile2[i]);
                         int cell = i * 4, gx = cell / G, gy = cell - gx * G;
                         if (s.oobx[gx]) v = neg4;
                         else {
@@ -638,7 +635,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                             if (s.ooby[gy + 3]) v.w = -1.0f;
                         }
                         __stcs(out4 + i, v);
-                        tile4[i] = zero4;
+                        tile2[i] = zero2;
                     }
                 }
                 __syncthreads();
@@ -680,6 +677,22 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                 const int gx = bin / G, gy = bin - gx * G;
                 const bool sent = which ? (K > 1) : true;
                 if (!(sent && (s.oobx[gx] || s.ooby[gy]))) out_a[(size_t)chn * GG + bin] = pt_val[tid];
+            }
+        }
+        if (others_tile && has && ch_others >= 0 && tid == 0) {
+            // crowded view (more than 32 other cells inside it): one thread adds the masses in (player,
+            // slot) order onto the zeros stored above — the same float sequence as the reference's `+=`
+            float* outc = out_a + (size_t)ch_others * GG;
+            for (int g = 0; g < p.KC; ++g) {
+                const float m = cm[g];
+                if (!(m > 0.0f) || (g >> 4) == a) continue;
+                const float dx = cxs[g] - cx, dy = cys[g] - cy;
+                if (fabsf(dx) > lim || fabsf(dy) > lim) continue;
+                const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
+                if (0 <= gx && gx < G && 0 <= gy && gy < G && !(K > 1 && (s.oobx[gx] || s.ooby[gy]))) {
+                    volatile float* q = outc + gx * G + gy;
+                    *q = *q + m;
+                }
             }
         }
         if (tid == 0) s.sc[SC_NOB] = 0;
@@ -738,7 +751,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         for (int i = tid; i < KC; i += nt) { s.cnt[i] = 0; s.eater[i] = NONE_I; s.gain[i] = 0.0f; }
         if (tid < 64) s.sc[tid] = 0;
         if (a.flags & F_STEP) {
-            for (int i = tid; i < c.num_pellets; i += nt) s.pwin[i] = NONE_I;
+            for (int i = tid; i < L.P_pad / 2; i += nt) reinterpret_cast<uint32_t*>(s.pwin)[i] = 0xFFFFFFFFu;
             for (int i = tid; i < L.P_pad / 32 + 1; i += nt) s.isx[i] = 0;
         }
     }
@@ -1001,14 +1014,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                             if (!(qx >= 0.0f)) continue;
                             const float ex = qx - x, ey = py[i] - y;
                             if (ex * ex + ey * ey < r2)
-                                if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
+                                if (claim_min16(&s.pwin[i], g)) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
                         }
                     }
                     for (int e = l4; e < nex; e += 4) {  // respawned since the hash was built (a stale hash
                         const int i = s.extras[e];       // entry of the same pellet may claim twice: atomicMin dedups)
                         const float ex = px[i] - x, ey = py[i] - y;
                         if (ex * ex + ey * ey < r2)
-                            if (atomicMin(&s.pwin[i], g) == NONE_I) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
+                            if (claim_min16(&s.pwin[i], g)) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
                     }
                 }
                 for (int f = tid; f < F; f += nt)
@@ -1024,7 +1037,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 for (int h = tid; h < nh; h += nt) {
                     const int i = s.hits[h];
                     const int g = s.pwin[i];
-                    s.pwin[i] = NONE_I;
+                    s.pwin[i] = NONE16;
                     atomicAdd(&s.cnt[g], 1);
                     ev_push(p, a, s, arena, tk, AGAR_EV_PELLET_EATEN, g, i);
                     float nx = -1.0f, ny = -1.0f;

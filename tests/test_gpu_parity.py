@@ -351,3 +351,34 @@ def test_ppo_loop_runs_and_snapshots_rerasterise_exactly(oracle):
     stats2 = tr.train_episode()
     assert np.isfinite(stats2["loss"]) and tr.sgd_steps == 4
     env.close()
+
+
+def test_raster_crowded_view_more_than_32_other_cells(oracle):
+    """More than 32 other cells inside one agent's view (sequential patch path) and several cells
+    per bin: bit-equal to the oracle, which is pinned to the reference extractor."""
+    import agarai_b200 as ab
+    rng = np.random.default_rng(11)
+    K, P = 6, 200
+    cfg = ab.default_config(num_arenas=3, num_agents=2, num_bots=K - 2, num_pellets=P, num_viruses=4, max_foods=8,
+                            grid_size=32, view_size=96.0, arena_size=300.0, obs_flags=31)
+    env = ab.BatchedAgarioEnv(cfg)
+    L = env.layout
+    rec = np.zeros((3, L.words), f32)
+    for n in range(3):
+        rec[n, L.pellet_x:L.pellet_x + L.P_pad] = -1; rec[n, L.food_x:L.food_x + L.F_pad] = -1
+        rec[n, L.pellet_x:L.pellet_x + P] = rng.uniform(0, 300, P); rec[n, L.pellet_y:L.pellet_y + P] = rng.uniform(0, 300, P)
+        rec[n, L.virus_x:L.virus_x + 4] = rng.uniform(100, 200, 4); rec[n, L.virus_y:L.virus_y + 4] = rng.uniform(100, 200, 4)
+        rec[n, L.food_x:L.food_x + 5] = rng.uniform(120, 180, 5); rec[n, L.food_y:L.food_y + 5] = rng.uniform(120, 180, 5)
+        centre = np.array([20.0, 150.0, 280.0])[n]  # corner / middle / far edge: sentinels in play
+        rec[n, L.cell_x:L.cell_x + K * 16] = np.clip(centre + rng.uniform(-30, 30, K * 16), 0, 300)
+        rec[n, L.cell_y:L.cell_y + K * 16] = np.clip(centre + rng.uniform(-30, 30, K * 16), 0, 300)
+        m = rng.uniform(5, 300, K * 16); m[rng.random(K * 16) < 0.1] = 0
+        rec[n, L.cell_m:L.cell_m + K * 16] = m
+        # clustered cells: many in the same bin
+        rec[n, L.cell_x + 40:L.cell_x + 60] = centre + 1.0; rec[n, L.cell_y + 40:L.cell_y + 60] = centre - 2.0
+    got = env.observe_records(torch.from_numpy(rec).cuda()).cpu().numpy()
+    ocfg = oracle.default_config(**_fields(cfg))
+    exp = oracle.OracleEnv(ocfg).observe_records(rec)
+    assert np.array_equal(got.view(np.int32), exp.view(np.int32))
+    assert (exp[:, :, 2] > 0).sum(axis=(2, 3)).max() > 20  # the others channel really is crowded
+    env.close()
