@@ -132,67 +132,60 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ------------------------------------------------------------- half-warp (one player) helpers
-// A player's 16 cell slots map to the 16 lanes of a half-warp: hmask names that half, hbase is
-// 0 or 16, slot = lane & 15.  Every lane of the half must call these together.
+// A player's 16 cell slots map to the 16 lanes of a half-warp: hbase is 0 or 16, slot = lane & 15.
+// All 32 lanes of the warp call these together (full-mask shuffles are single SHFL instructions;
+// partial masks that differ across the warp compile to a MATCH.ANY sequence per operation), so the
+// callers keep their control flow warp-uniform and pass mass 0 for lanes without a cell.
+#define FULL 0xffffffffu
 
-// numpy's pairwise add-reduce over the first n (<=16) lanes of the half, see np_sum16 in the oracle
-__device__ __forceinline__ float hw_np_sum(unsigned hmask, int hbase, int slot, float a, int n) {
-    float res;
-    if (n < 8) {
-        res = 0.0f;
-        for (int i = 0; i < 7; ++i) {
-            float v = __shfl_sync(hmask, a, hbase + i);
-            if (i < n) res = res + v;
-        }
-    } else {
-        float hi = __shfl_sync(hmask, a, hbase + ((slot + 8) & 15));
-        float r = (n == 16) ? a + hi : a;
-        r = r + __shfl_xor_sync(hmask, r, 1);
-        r = r + __shfl_xor_sync(hmask, r, 2);
-        r = r + __shfl_xor_sync(hmask, r, 4);
-        res = __shfl_sync(hmask, r, hbase);
-        if (n < 16)
-            for (int i = 8; i < 15; ++i) {
-                float v = __shfl_sync(hmask, a, hbase + i);
-                if (i < n) res = res + v;
-            }
+// numpy's pairwise add-reduce over the first n (<=16) lanes of the half, see np_sum16 in the oracle.
+// Both of numpy's code paths are evaluated without branches and the one for n is selected.
+__device__ __forceinline__ float hw_np_sum(int hbase, int slot, float a, int n) {
+    float seq = 0.0f;  // n < 8: sequential from 0
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        float v = __shfl_sync(FULL, a, hbase + i);
+        if (i < n) seq = seq + v;
     }
-    return res;
+    // n >= 8: eight accumulators, tree, remainder
+    float hi = __shfl_sync(FULL, a, hbase + ((slot + 8) & 15));
+    float r = (n == 16) ? a + hi : a;
+    r = r + __shfl_xor_sync(FULL, r, 1);
+    r = r + __shfl_xor_sync(FULL, r, 2);
+    r = r + __shfl_xor_sync(FULL, r, 4);
+    float pw = __shfl_sync(FULL, r, hbase);
+#pragma unroll
+    for (int i = 8; i < 15; ++i) {
+        float v = __shfl_sync(FULL, a, hbase + i);
+        if (i < n && n < 16) pw = pw + v;
+    }
+    return n < 8 ? seq : pw;
 }
 
-// features/extractors.py:207-212 `position` in numpy float32 evaluation order
-__device__ __forceinline__ bool hw_centroid(unsigned hmask, int hbase, int slot, float x, float y, float m,
-                                            float& cx, float& cy) {
-    unsigned alive = (__ballot_sync(hmask, m > 0.0f) >> hbase) & 0xFFFFu;
-    int n = __popc(alive);
+// features/extractors.py:207-212 `position` in numpy float32 evaluation order; false if no cell
+__device__ __forceinline__ bool hw_centroid(int hbase, int slot, float x, float y, float m, float& cx, float& cy) {
+    const unsigned alive = (__ballot_sync(FULL, m > 0.0f) >> hbase) & 0xFFFFu;
+    const int n = __popc(alive);
+    const unsigned src = __fns(alive, 0, slot + 1);
+    const int srcl = (slot < n) ? (int)src : 0;
+    const float w = __shfl_sync(FULL, m, hbase + srcl);
+    const float xs = __shfl_sync(FULL, x, hbase + srcl);
+    const float ys = __shfl_sync(FULL, y, hbase + srcl);
+    const float den = hw_np_sum(hbase, slot, w, n);
+    const float nx = hw_np_sum(hbase, slot, xs * w, n);
+    const float ny = hw_np_sum(hbase, slot, ys * w, n);
     if (n == 0) return false;
-    if (n == 1) {  // np.average over one cell is (x*m)/m: what the general path below evaluates to
-        const int src1 = hbase + __ffs(alive) - 1;
-        const float w1 = __shfl_sync(hmask, m, src1);
-        cx = (__shfl_sync(hmask, x, src1) * w1) / w1;
-        cy = (__shfl_sync(hmask, y, src1) * w1) / w1;
-        return true;
-    }
-    unsigned src = __fns(alive, 0, slot + 1);
-    int srcl = (slot < n) ? (int)src : 0;
-    float w = __shfl_sync(hmask, m, hbase + srcl);
-    float xs = __shfl_sync(hmask, x, hbase + srcl);
-    float ys = __shfl_sync(hmask, y, hbase + srcl);
-    float xw = xs * w, yw = ys * w;
-    float den = hw_np_sum(hmask, hbase, slot, w, n);
-    float nx = hw_np_sum(hmask, hbase, slot, xw, n);
-    float ny = hw_np_sum(hmask, hbase, slot, yw, n);
     cx = nx / den;
     cy = ny / den;
     return true;
 }
 
 // butterfly 8,4,2,1 sum of the 16 slots (treesum16 in the oracle); result valid in every lane
-__device__ __forceinline__ float hw_treesum(unsigned hmask, float v) {
-    v = v + __shfl_xor_sync(hmask, v, 8);
-    v = v + __shfl_xor_sync(hmask, v, 4);
-    v = v + __shfl_xor_sync(hmask, v, 2);
-    v = v + __shfl_xor_sync(hmask, v, 1);
+__device__ __forceinline__ float hw_treesum(float v) {
+    v = v + __shfl_xor_sync(FULL, v, 8);
+    v = v + __shfl_xor_sync(FULL, v, 4);
+    v = v + __shfl_xor_sync(FULL, v, 2);
+    v = v + __shfl_xor_sync(FULL, v, 1);
     return v;
 }
 
@@ -301,15 +294,13 @@ __device__ __forceinline__ Smem carve(float* base, const AgarLayout& L, int G) {
 }
 
 // -------------------------------------------------------------------------------- events
+__device__ __forceinline__ void ev_push_slow(int* counter, int32_t* events, int cap, int arena, int tick, int type, int x, int y) {
+    int i = atomicAdd(counter, 1);
+    if (i < cap) *reinterpret_cast<int4*>(events + ((size_t)arena * cap + i) * 4) = make_int4(tick, type, x, y);
+}
 __device__ __forceinline__ void ev_push(const DevParams& p, const KArgs& a, const Smem& s, int arena, int tick,
                                         int type, int x, int y) {
-    int cap = p.c.event_capacity;
-    if (cap <= 0) return;
-    int i = atomicAdd(&s.sc[SC_EVCOUNT], 1);
-    if (i < cap) {
-        int4 e = make_int4(tick, type, x, y);
-        *reinterpret_cast<int4*>(a.events + ((size_t)arena * cap + i) * 4) = e;
-    }
+    if (p.c.event_capacity > 0) ev_push_slow(&s.sc[SC_EVCOUNT], a.events, p.c.event_capacity, arena, tick, type, x, y);
 }
 
 // ----------------------------------------------------------------------------- sub-phases
@@ -466,7 +457,6 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
     const AgarLayout& L = p.L;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const int hbase = lane & 16, slot = lane & 15;
-    const unsigned hmask = 0xFFFFu << hbase;
     const int G = p.c.grid_size, GG = G * G, A = p.c.num_agents, K = p.K;
     const float arena = p.c.arena_size, lim = p.raster_lim;
     const int half = G / 2;
@@ -482,11 +472,12 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
         for (int i = tid; i < GG / 8; i += nt) t4[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     // centroids of all agents (half-warp per agent)
-    for (int g = tid; g < A * MC; g += nt) {
-        int k = g >> 4;
+    for (int base = 0; base < A * MC; base += nt) {  // warp-uniform: every lane takes part in the shuffles
+        const int g = base + tid;
+        const bool valid = g < A * MC;
         float cx = 0.0f, cy = 0.0f;
-        bool has = hw_centroid(hmask, hbase, slot, cxs[g], cys[g], cm[g], cx, cy);
-        if (slot == 0) { s.Cx[k] = cx; s.Cy[k] = cy; s.palive[k] = has ? 1 : 0; }
+        const bool has = hw_centroid(hbase, slot, valid ? cxs[g] : 0.0f, valid ? cys[g] : 0.0f, valid ? cm[g] : 0.0f, cx, cy);
+        if (valid && slot == 0) { s.Cx[g >> 4] = cx; s.Cy[g >> 4] = cy; s.palive[g >> 4] = has ? 1 : 0; }
     }
     if (tid == 0) s.sc[SC_NOB] = 0;
     // write-out geometry: when 4*nt is a multiple of G a thread keeps its 4 columns and walks rows
@@ -722,7 +713,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     const Smem s = carve(smem_raw, L, c.grid_size);
     const int tid = threadIdx.x, nt = kThreads, lane = tid & 31;
     const int hbase = lane & 16, slot = lane & 15;
-    const unsigned hmask = 0xFFFFu << hbase;
     const int arena = blockIdx.x;
     const int A = c.num_agents, K = p.K, KC = p.KC, V = c.num_viruses, F = c.max_foods;
     const uint64_t gid64 = (uint64_t)(c.arena_id_base + arena);
@@ -809,14 +799,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         __syncthreads();
         // ---- players with several cells: numpy-order centroid and butterfly mass (half-warp per player) ----
         if (s.sc[SC_MULTI]) {
-            for (int g = tid; g < KC; g += nt) {
-                const int k = g >> 4;
-                if (__popc((unsigned)s.pmask[k]) < 2) continue;  // uniform per half-warp
-                const float m = cm[g];
+            for (int base = 0; base < KC; base += nt) {
+                const int g = base + tid, k = g >> 4;
+                const bool multi = g < KC && __popc((unsigned)s.pmask[k]) >= 2;
+                if (!__any_sync(FULL, multi)) continue;  // warp-uniform
+                const float m = multi ? cm[g] : 0.0f;
                 float Cx = 0.0f, Cy = 0.0f;
-                hw_centroid(hmask, hbase, slot, cx[g], cy[g], m, Cx, Cy);
-                const float mb = hw_treesum(hmask, m);
-                if (slot == 0) { s.Cx[k] = Cx; s.Cy[k] = Cy; if (k < A) s.mass0[k] = mb; }
+                hw_centroid(hbase, slot, multi ? cx[g] : 0.0f, multi ? cy[g] : 0.0f, m, Cx, Cy);
+                const float mb = hw_treesum(m);
+                if (multi && slot == 0) { s.Cx[k] = Cx; s.Cy[k] = Cy; if (k < A) s.mass0[k] = mb; }
             }
             __syncthreads();
         }
@@ -848,9 +839,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         //      per bot search the 3x3 bins around it; the result is final when it is closer than the
         //      nearest unsearched bin edge, otherwise the whole window is searched ----
         {
-            const unsigned qmask = 0xFu << (lane & ~3);
             const int l4 = lane & 3;
-            for (int k = A + (tid >> 2); k < K; k += nt >> 2) {
+            for (int kb = A + (tid >> 5) * 8; kb < K; kb += nt >> 2) {  // 8 bots per warp pass, warp-uniform
+                const int k = min(kb + (lane >> 2), K - 1);
+                const bool valid = kb + (lane >> 2) < K;
                 const float Cx = s.Cx[k], Cy = s.Cy[k], R = c.bot_sense_radius;
                 const int bx = hash_coord(p, Cx), by = hash_coord(p, Cy);
                 int x0 = max(bx - 1, 0), x1 = min(bx + 1, HASH_W - 1), y0 = max(by - 1, 0), y1 = min(by + 1, HASH_W - 1);
@@ -881,11 +873,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     }
 #pragma unroll
                     for (int o = 2; o > 0; o >>= 1) {
-                        float ob = __shfl_xor_sync(qmask, best, o);
-                        int oi = __shfl_xor_sync(qmask, bi, o);
+                        float ob = __shfl_xor_sync(FULL, best, o);
+                        int oi = __shfl_xor_sync(FULL, bi, o);
                         if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
                     }
-                    if (pass == 1) break;
+                    if (pass == 1) break;  // warp-uniform: `pass` only advances together (see below)
                     // distance from the bot to the nearest edge of the searched block that has bins beyond it
                     float margin = INFINITY;
                     if (x0 > 0) margin = fminf(margin, Cx - (float)x0 * p.hash_bs);
@@ -893,14 +885,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     if (y0 > 0) margin = fminf(margin, Cy - (float)y0 * p.hash_bs);
                     if (y1 < HASH_W - 1) margin = fminf(margin, (float)(y1 + 1) * p.hash_bs - Cy);
                     const float safe = margin * 0.999f - 0.01f;
-                    const bool done = (bi != NONE_I && safe > 0.0f && best < safe * safe) || safe >= R * 1.5f;
-                    if (done) break;  // uniform inside the quad (all four lanes hold the reduced result)
+                    const bool done = !valid || (bi != NONE_I && safe > 0.0f && best < safe * safe) || safe >= R * 1.5f;
+                    if (__all_sync(FULL, done)) break;  // warp-uniform exit
+                    if (done) { x0 = 1; x1 = 0; y0 = 1; y1 = 0; continue; }  // this quad keeps its result: empty second pass
                     const float Rp = R * 1.001f + 0.01f;
                     x0 = hash_coord(p, Cx - Rp); x1 = hash_coord(p, Cx + Rp);
                     y0 = hash_coord(p, Cy - Rp); y1 = hash_coord(p, Cy + Rp);
                     best = INFINITY; bi = NONE_I;
                 }
-                if (l4 == 0) {
+                if (valid && l4 == 0) {
                     if (bi != NONE_I) { s.Tx[k] = px[bi]; s.Ty[k] = py[bi]; }
                     else {
                         uint32_t epoch = tick0 & ~(uint32_t)(c.bot_roam_period - 1);
@@ -914,13 +907,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         __syncthreads();
         // ---- split: i-th eligible cell -> i-th free slot (ballot ranks inside the half-warp) ----
         if (s.sc[SC_ANYSPLIT]) {
-            for (int g = tid; g < A * MC; g += nt) {
-                const int k = g >> 4;
-                if (s.pact[k] != AGAR_ACT_SPLIT) continue;  // uniform per half-warp
-                float m = cm[g];
-                unsigned freeb = (__ballot_sync(hmask, m == 0.0f) >> hbase) & 0xFFFFu;
-                bool elig = m >= c.split_min_mass;
-                unsigned eligb = (__ballot_sync(hmask, elig) >> hbase) & 0xFFFFu;
+            for (int base = 0; base < A * MC; base += nt) {
+                const int g = base + tid, k = g >> 4;
+                const bool splitting = g < A * MC && s.pact[k] == AGAR_ACT_SPLIT;
+                if (!__any_sync(FULL, splitting)) continue;  // warp-uniform
+                float m = splitting ? cm[g] : -1.0f;
+                unsigned freeb = (__ballot_sync(FULL, m == 0.0f) >> hbase) & 0xFFFFu;
+                bool elig = splitting && m >= c.split_min_mass;
+                unsigned eligb = (__ballot_sync(FULL, elig) >> hbase) & 0xFFFFu;
                 int i = __popc(eligb & ((1u << slot) - 1u));
                 if (elig && i < __popc(freeb)) {
                     int d = k * MC + (int)__fns(freeb, 0, i + 1);
@@ -980,15 +974,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 const int n = s.sc[SC_NLIST];
                 const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
                 const int l4 = lane & 3;
-                for (int q = tid >> 2; q < n; q += nt >> 2) {
-                    const int g = s.list[q];
-                    const float m = cm[g];
-                    if (!(m > 0.0f)) continue;  // died earlier in this step
+                for (int qb = (tid >> 5) * 8; qb < n; qb += nt >> 2) {  // 8 cells per warp pass, warp-uniform
+                    const int q = qb + (lane >> 2);
+                    const int g = q < n ? s.list[q] : s.list[0];
+                    const float m = q < n ? cm[g] : 0.0f;
+                    const float ox = cx[g], oy = cy[g], oix = cix[g], oiy = ciy[g], t = ct[g];
+                    __syncwarp();  // lane 0 of a quad stores the cell below: its whole quad has read it by now
+                    if (!(m > 0.0f)) continue;  // no cell, or it died earlier in this step
                     const int k = g >> 4;
                     const float r2 = m * r2pm;
                     const float r = sqrtf(r2);
                     float spd = c.speed_k / sqrtf(r);
-                    const float ox = cx[g], oy = cy[g], oix = cix[g], oiy = ciy[g], t = ct[g];
                     float dx = s.Tx[k] - ox, dy = s.Ty[k] - oy;
                     float d = sqrtf(dx * dx + dy * dy);
                     float den = d > c.target_reach ? d : c.target_reach;
@@ -998,7 +994,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     float ix = oix * c.impulse_decay, iy = oiy * c.impulse_decay;
                     if (fabsf(ix) < 1e-3f && fabsf(iy) < 1e-3f) { ix = 0.0f; iy = 0.0f; }
                     const float x = clampf(nx, 0.0f, arena_size), y = clampf(ny, 0.0f, arena_size);
-                    __syncwarp(0xFu << (lane & ~3));  // the quad has read the old state
                     if (l4 == 0) {
                         cx[g] = x; cy[g] = y; cix[g] = ix; ciy[g] = iy;
                         if (t > 0.0f) ct[g] = t - 1.0f;
@@ -1024,6 +1019,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                             if (claim_min16(&s.pwin[i], g)) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
                     }
                 }
+#pragma unroll 1
                 for (int f = tid; f < F; f += nt)
                     if (fx[f] >= 0.0f) s.sc[SC_FOODANY] = 1;
                 for (int v = tid; v < V; v += nt) s.vwin[v] = NONE_I;
@@ -1089,11 +1085,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             // scanning a quarter of the possible eaters; the lowest gid wins
             auto eat_test = [&]() {
                 const int n = s.sc[SC_NLIST];
-                const unsigned qmask = 0xFu << (lane & ~3);
                 const int l4 = lane & 3;
-                for (int q = tid >> 2; q < n; q += nt >> 2) {
-                    const int j = s.list[q];
-                    const float mj = cm[j];
+                for (int qb = (tid >> 5) * 8; qb < n; qb += nt >> 2) {  // 8 preys per warp pass, warp-uniform
+                    const int q = qb + (lane >> 2);
+                    const int j = q < n ? s.list[q] : s.list[0];
+                    const float mj = q < n ? cm[j] : 0.0f;
                     const float need = mj * c.eat_ratio, x = cx[j], y = cy[j];
                     const int kj = j >> 4;
                     int best = NONE_I;
@@ -1107,8 +1103,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                             if (dx * dx + dy * dy < mi * r2pm && i < best) best = i;
                         }
                     }
-                    best = min(best, __shfl_xor_sync(qmask, best, 1));
-                    best = min(best, __shfl_xor_sync(qmask, best, 2));
+                    best = min(best, __shfl_xor_sync(FULL, best, 1));
+                    best = min(best, __shfl_xor_sync(FULL, best, 2));
                     if (l4 == 0 && best != NONE_I) { s.eater[j] = best; s.sc[SC_ANYEAT] = 1; }
                 }
             };
@@ -1149,6 +1145,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 // one thread per player walks its slots in order (free slots are consumed sequentially
                 // inside a player, exactly as the oracle does)
                 for (int k = tid; k < K; k += nt) {
+#pragma unroll 1
                     for (int sl = 0; sl < MC; ++sl) {
                         const int g = k * MC + sl;
                         const int v = s.eater[g];
@@ -1156,6 +1153,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                         s.eater[g] = NONE_I;
                         float m1 = cm[g] + c.virus_mass;
                         int freeslot[MC]; int nfree = 0;
+#pragma unroll 1
                         for (int q = 0; q < MC; ++q)
                             if (cm[k * MC + q] == 0.0f) freeslot[nfree++] = q;
                         int np = nfree < c.pop_pieces ? nfree : c.pop_pieces;
@@ -1165,6 +1163,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                             float keep = m1 * 0.5f;
                             float piece = (m1 - keep) / (float)np;
                             cm[g] = keep; ct[g] = c.merge_delay;
+#pragma unroll 1
                             for (int j = 0; j < np; ++j) {
                                 int d = k * MC + freeslot[j];
                                 cx[d] = cx[g]; cy[d] = cy[g];
@@ -1221,16 +1220,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             }
             // ---- merge own cells whose timers ran out (half-warp per player, shuffles) ----
             if (s.sc[SC_MULTI]) {
-                for (int g = tid; g < KC; g += nt) {
-                    const float m = cm[g], t = ct[g], x = cx[g], y = cy[g];
+                for (int base = 0; base < KC; base += nt) {
+                    const int g = base + tid;
+                    const bool valid = g < KC;
+                    const float m = valid ? cm[g] : 0.0f, t = valid ? ct[g] : 1.0f, x = valid ? cx[g] : 0.0f, y = valid ? cy[g] : 0.0f;
                     const bool can = m > 0.0f && t == 0.0f;
-                    unsigned canb = (__ballot_sync(hmask, can) >> hbase) & 0xFFFFu;
-                    if (__popc(canb) < 2) continue;  // uniform per half-warp
+                    unsigned canb = (__ballot_sync(FULL, can) >> hbase) & 0xFFFFu;
+                    if (!__any_sync(FULL, __popc(canb) >= 2)) continue;  // warp-uniform
                     const float r2 = m * r2pm;
                     int root = slot;
+#pragma unroll 1
                     for (int q = 0; q < MC - 1; ++q) {
-                        float xa = __shfl_sync(hmask, x, hbase + q), ya = __shfl_sync(hmask, y, hbase + q);
-                        float ra = __shfl_sync(hmask, r2, hbase + q);
+                        float xa = __shfl_sync(FULL, x, hbase + q), ya = __shfl_sync(FULL, y, hbase + q);
+                        float ra = __shfl_sync(FULL, r2, hbase + q);
                         if (can && root == slot && q < slot && ((canb >> q) & 1u)) {
                             float dx = x - xa, dy = y - ya;
                             float rr = ra > r2 ? ra : r2;
@@ -1239,13 +1241,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     }
                     // follow partners down to the final survivor (partner < slot, so 4 jumps suffice)
 #pragma unroll
-                    for (int it = 0; it < 4; ++it) root = __shfl_sync(hmask, root, hbase + root);
-                    unsigned merged = (__ballot_sync(hmask, root != slot) >> hbase) & 0xFFFFu;
-                    if (merged == 0u) continue;
+                    for (int it = 0; it < 4; ++it) root = __shfl_sync(FULL, root, hbase + root);
+                    unsigned merged = (__ballot_sync(FULL, root != slot) >> hbase) & 0xFFFFu;
+                    if (!__any_sync(FULL, merged != 0u)) continue;  // warp-uniform
                     float acc = m;
+#pragma unroll 1
                     for (int q = 1; q < MC; ++q) {
-                        float mq = __shfl_sync(hmask, m, hbase + q);
-                        int rq = __shfl_sync(hmask, root, hbase + q);
+                        float mq = __shfl_sync(FULL, m, hbase + q);
+                        int rq = __shfl_sync(FULL, root, hbase + q);
                         if (rq == slot && q != slot) acc = acc + mq;
                     }
                     if (root != slot) {
@@ -1260,12 +1263,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         }
 
         // ---- rewards / dones ----
-        for (int g = tid; g < A * MC; g += nt) {
-            const int k = g >> 4;
-            float m = cm[g];
-            float after = hw_treesum(hmask, m);
-            bool alive = __ballot_sync(hmask, m > 0.0f) != 0u;
-            if (slot == 0) {
+        for (int base = 0; base < A * MC; base += nt) {
+            const int g = base + tid, k = g >> 4;
+            const bool valid = g < A * MC;
+            float m = valid ? cm[g] : 0.0f;
+            float after = hw_treesum(m);
+            bool alive = ((__ballot_sync(FULL, m > 0.0f) >> hbase) & 0xFFFFu) != 0u;
+            if (valid && slot == 0) {
                 int was = s.reci[L.agent_done + k];
                 float rw = was ? 0.0f : after - s.mass0[k];
                 if (!was && !alive) {
