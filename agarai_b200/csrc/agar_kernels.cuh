@@ -472,8 +472,8 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
         for (int i = tid; i < GG / 8; i += nt) t4[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     // centroids of all agents (half-warp per agent)
-    for (int base = 0; base < A * MC; base += nt) {  // warp-uniform: every lane takes part in the shuffles
-        const int g = base + tid;
+    for (int base = (tid & ~31); base < A * MC; base += nt) {  // warp-uniform; warps without a valid lane skip
+        const int g = base + lane;
         const bool valid = g < A * MC;
         float cx = 0.0f, cy = 0.0f;
         const bool has = hw_centroid(hbase, slot, valid ? cxs[g] : 0.0f, valid ? cys[g] : 0.0f, valid ? cm[g] : 0.0f, cx, cy);
@@ -799,8 +799,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         __syncthreads();
         // ---- players with several cells: numpy-order centroid and butterfly mass (half-warp per player) ----
         if (s.sc[SC_MULTI]) {
-            for (int base = 0; base < KC; base += nt) {
-                const int g = base + tid, k = g >> 4;
+            for (int base = (tid & ~31); base < KC; base += nt) {
+                const int g = base + lane, k = g >> 4;
                 const bool multi = g < KC && __popc((unsigned)s.pmask[k]) >= 2;
                 if (!__any_sync(FULL, multi)) continue;  // warp-uniform
                 const float m = multi ? cm[g] : 0.0f;
@@ -907,8 +907,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         __syncthreads();
         // ---- split: i-th eligible cell -> i-th free slot (ballot ranks inside the half-warp) ----
         if (s.sc[SC_ANYSPLIT]) {
-            for (int base = 0; base < A * MC; base += nt) {
-                const int g = base + tid, k = g >> 4;
+            for (int base = (tid & ~31); base < A * MC; base += nt) {
+                const int g = base + lane, k = g >> 4;
                 const bool splitting = g < A * MC && s.pact[k] == AGAR_ACT_SPLIT;
                 if (!__any_sync(FULL, splitting)) continue;  // warp-uniform
                 float m = splitting ? cm[g] : -1.0f;
@@ -1220,8 +1220,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             }
             // ---- merge own cells whose timers ran out (half-warp per player, shuffles) ----
             if (s.sc[SC_MULTI]) {
-                for (int base = 0; base < KC; base += nt) {
-                    const int g = base + tid;
+                for (int base = (tid & ~31); base < KC; base += nt) {
+                    const int g = base + lane;
                     const bool valid = g < KC;
                     const float m = valid ? cm[g] : 0.0f, t = valid ? ct[g] : 1.0f, x = valid ? cx[g] : 0.0f, y = valid ? cy[g] : 0.0f;
                     const bool can = m > 0.0f && t == 0.0f;
@@ -1263,8 +1263,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         }
 
         // ---- rewards / dones ----
-        for (int base = 0; base < A * MC; base += nt) {
-            const int g = base + tid, k = g >> 4;
+        for (int base = (tid & ~31); base < A * MC; base += nt) {
+            const int g = base + lane, k = g >> 4;
             const bool valid = g < A * MC;
             float m = valid ? cm[g] : 0.0f;
             float after = hw_treesum(m);
