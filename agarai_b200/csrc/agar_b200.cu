@@ -61,6 +61,7 @@ size_t obs_elems(const AgarEnv* e) {
 int launch(AgarEnv* e, KArgs& a, int n_records, cudaStream_t st) {
     a.n_records = n_records;
     switch (e->min_blocks) {
+        case 8: agar_step_kernel<kThreads, 8><<<n_records, kThreads, e->smem, st>>>(e->p, a); break;
         case 7: agar_step_kernel<kThreads, 7><<<n_records, kThreads, e->smem, st>>>(e->p, a); break;
         case 6: agar_step_kernel<kThreads, 6><<<n_records, kThreads, e->smem, st>>>(e->p, a); break;
         default: agar_step_kernel<kThreads, 5><<<n_records, kThreads, e->smem, st>>>(e->p, a); break;
@@ -142,7 +143,12 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
     }
     // CTAs per SM that the shared memory allows (1 KB per CTA is reserved by the system)
     const int fit = (int)((size_t)prop.sharedMemPerMultiprocessor / (e->smem + 1024));
-    e->min_blocks = fit >= 7 ? 7 : (fit == 6 ? 6 : 5);
+    e->min_blocks = fit >= 8 ? 8 : (fit == 7 ? 7 : (fit == 6 ? 6 : 5));
+    if (const char* mb = std::getenv("AGAR_MIN_BLOCKS")) {  // tuning switch: force a register budget (5..8 CTAs/SM)
+        const int v = std::atoi(mb);
+        if (v >= 5 && v <= 8) e->min_blocks = v;
+    }
+    CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));

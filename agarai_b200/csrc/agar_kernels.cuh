@@ -77,12 +77,18 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 __device__ __forceinline__ float u01(uint32_t u) { return (float)(u >> 8) * (1.0f / 16777216.0f); }
 
+// Out of line on purpose: random positions are drawn on rare paths (respawns, resets), and one copy of
+// the ten Philox rounds keeps the hot path of the step kernel small (the SM's instruction cache is 32 KB).
+__device__ __noinline__ float2 rand_pos2(uint32_t slot, uint32_t stream, uint32_t tick, uint32_t gid_lo, uint32_t k0,
+                                         uint32_t k1, float arena_size) {
+    uint32_t o0, o1;
+    philox4x32_10(slot, stream, tick, gid_lo, k0, k1, o0, o1);
+    return make_float2(u01(o0) * arena_size, u01(o1) * arena_size);
+}
 __device__ __forceinline__ void rand_pos(const DevParams& p, uint32_t gid_lo, uint32_t gid_hi, uint32_t slot,
                                          uint32_t stream, uint32_t tick, float& x, float& y) {
-    uint32_t o0, o1;
-    philox4x32_10(slot, stream, tick, gid_lo, p.seed_lo, p.seed_hi ^ gid_hi, o0, o1);
-    x = u01(o0) * p.c.arena_size;
-    y = u01(o1) * p.c.arena_size;
+    const float2 r = rand_pos2(slot, stream, tick, gid_lo, p.seed_lo, p.seed_hi ^ gid_hi, p.c.arena_size);
+    x = r.x; y = r.y;
 }
 
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -98,6 +104,11 @@ __device__ __forceinline__ bool claim_min16(uint16_t* addr, int g) {
     }
     return false;
 }
+
+// two 16-bit event counters per word (a cell cannot eat more than P <= 8192 pellets in a tick)
+__device__ __forceinline__ void cnt_inc(uint32_t* cnt32, int g) { atomicAdd(&cnt32[g >> 1], (g & 1) ? 0x10000u : 1u); }
+__device__ __forceinline__ int cnt_get(const uint32_t* cnt32, int g) { return reinterpret_cast<const uint16_t*>(cnt32)[g]; }
+__device__ __forceinline__ void cnt_clear(uint32_t* cnt32, int g) { reinterpret_cast<uint16_t*>(cnt32)[g] = 0; }
 
 // ------------------------------------------------------------- TMA bulk copies (1-D) + mbarrier
 // The arena record and its persisted pellet hash are contiguous blocks of global memory: one thread
@@ -163,7 +174,9 @@ __device__ __forceinline__ float hw_np_sum(int hbase, int slot, float a, int n) 
 }
 
 // features/extractors.py:207-212 `position` in numpy float32 evaluation order; false if no cell
-__device__ __forceinline__ bool hw_centroid(int hbase, int slot, float x, float y, float m, float& cx, float& cy) {
+struct Centroid { float x, y; int ok; };
+__device__ __noinline__ Centroid hw_centroid_ool(int hbase, int slot, float x, float y, float m) {
+    Centroid r; r.x = 0.0f; r.y = 0.0f; r.ok = 0;
     const unsigned alive = (__ballot_sync(FULL, m > 0.0f) >> hbase) & 0xFFFFu;
     const int n = __popc(alive);
     const unsigned src = __fns(alive, 0, slot + 1);
@@ -174,10 +187,16 @@ __device__ __forceinline__ bool hw_centroid(int hbase, int slot, float x, float 
     const float den = hw_np_sum(hbase, slot, w, n);
     const float nx = hw_np_sum(hbase, slot, xs * w, n);
     const float ny = hw_np_sum(hbase, slot, ys * w, n);
-    if (n == 0) return false;
-    cx = nx / den;
-    cy = ny / den;
-    return true;
+    if (n == 0) return r;
+    r.x = nx / den;
+    r.y = ny / den;
+    r.ok = 1;
+    return r;
+}
+__device__ __forceinline__ bool hw_centroid(int hbase, int slot, float x, float y, float m, float& cx, float& cy) {
+    const Centroid r = hw_centroid_ool(hbase, slot, x, y, m);  // all 32 lanes call together
+    if (r.ok) { cx = r.x; cy = r.y; }
+    return r.ok != 0;
 }
 
 // butterfly 8,4,2,1 sum of the 16 slots (treesum16 in the oracle); result valid in every lane
@@ -191,12 +210,12 @@ __device__ __forceinline__ float hw_treesum(float v) {
 
 // ------------------------------------------------------------------------- shared memory map
 // Pellet hash: HASH_W x HASH_W uniform grid over the arena, built by counting sort once per step
-// (and again only if more than EXTRA_CAP pellets respawned since).  It lives in the same shared
-// memory as the observation tile, which is only needed after the last tick.
+// (and again only if more than EXTRA_CAP pellets respawned since).
 #define HASH_W 16
 #define HASH_BINS (HASH_W * HASH_W)
 #define EXTRA_CAP 16    // pellets that may respawn before the hash is rebuilt (each is checked by every cell)
 #define HASH_HDR 4      // words of the persisted hash header: {epoch, nextras, 0, 0}
+#define HITS_CAP 128    // claimed pellets listed per tick
 
 struct Smem {
     float* rec;       // [words] the arena record
@@ -208,21 +227,21 @@ struct Smem {
     int32_t* hhdr;    // [HASH_HDR]    header of the persisted hash record: {epoch, nextras, 0, 0}
     uint64_t* mbar;   // mbarrier for the bulk copies (2 words)
     int32_t* isx;     // [P_pad/32+1]  bit per pellet: respawned since the hash was built
-    // union: the observation tile (only needed after the last tick) over the per-tick scratch
-    uint32_t* tile;   // [G*G/2] one count channel, two 16-bit bins per word (exact integer atomics)
+    // per-tick scratch
     int32_t* hcur;    // [HASH_BINS]   counting-sort cursors (only while the hash is built)
     uint16_t* pwin;   // [P_pad]       winner cell of each pellet this tick (16-bit CAS-min), NONE16 = unclaimed
-    uint16_t* hits;   // [P_pad]       pellets claimed this tick (bin cache while the hash is built)
-    int32_t* list;    // [KC] gids of the alive cells (unordered)
-    int32_t* cnt;     // [KC] pellets / foods eaten this tick
-    int32_t* eater;   // [KC] lowest-gid cell that eats this one / first virus won (NONE_I between uses)
-    float* gain;      // [KC]
+                      //               (bin cache while the hash is built)
+    uint16_t* hits;   // [HITS_CAP]    pellets claimed this tick; past the capacity the resolver scans pwin
+    uint16_t* list;   // [KC] gids of the alive cells (unordered)
+    uint32_t* cnt32;  // [KC/2] pellets / foods eaten this tick, two 16-bit counters per word
+    uint16_t* eater;  // [KC] lowest-gid cell that eats this one / first virus won (NONE16 between uses)
+    float* gain;      // [max(KC, F_pad+4)] (doubles as the free-food-slot list of the feed phase)
     int32_t* vwin;    // [V_pad]
-    float *Tx, *Ty, *dirx, *diry, *Cx, *Cy, *mass0;  // [K_pad] each
-    int32_t *pact, *palive, *pmask;                  // [K_pad]
-    uint8_t *oobx, *ooby;                            // [128]
-    int32_t* freefood;                               // [F_pad]
-    int32_t* rb;                                     // [256] raster: in-view cell entities and patches
+    float *Tx, *Ty, *Cx, *Cy;                        // [K_pad] each
+    int32_t *palive, *pmask;                         // [K_pad]
+    float *dirx, *diry, *mass0;                      // [A_pad] (agents only)
+    int32_t* pact;                                   // [A_pad]
+    int32_t* rb;                                     // [96] raster: other players' cells in view
     int32_t* sc;                                     // [32] scalars + [32] list-membership bitmask
 };
 enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT, SC_EVCOUNT, SC_RESET, SC_ALLDONE,
@@ -230,12 +249,17 @@ enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT,
 static_assert(SC_COUNT <= 32, "scalar slots overlap the list-membership bitmask");
 
 __host__ __device__ inline size_t pad4z(size_t n) { return (n + 3) & ~(size_t)3; }
+__host__ __device__ inline size_t gain_words(const AgarLayout& L) {
+    const size_t a = (size_t)L.cells_total, b = (size_t)L.F_pad + 4;
+    return a > b ? a : b;
+}
 __host__ __device__ inline size_t scratch_words(const AgarLayout& L) {
-    return HASH_BINS + (size_t)L.P_pad / 2 + (size_t)L.P_pad / 2 + (size_t)L.cells_total * 4;
+    // hcur | pwin | hits | list, eater (16-bit) | cnt32 | gain
+    return HASH_BINS + (size_t)L.P_pad / 2 + HITS_CAP / 2 + (size_t)L.cells_total + (size_t)L.cells_total / 2 + gain_words(L);
 }
 __host__ __device__ inline size_t union_words(const AgarLayout& L, int G) {
-    size_t a = scratch_words(L), t = (size_t)G * G / 2;
-    return pad4z(a > t ? a : t);
+    (void)G;  // the observation needs no shared-memory tile: it is written from registers and patched in place
+    return pad4z(scratch_words(L));
 }
 __host__ __device__ inline size_t kpad(const AgarLayout& L) { return pad4z((size_t)L.num_players); }
 
@@ -249,12 +273,10 @@ __host__ __device__ inline size_t smem_bytes(const AgarLayout& L, int G) {
     size_t w = 0;
     w += (size_t)L.words;                                   // rec
     w += HASH_BINS + 4 + pad4z((size_t)L.P_pad / 2) + EXTRA_CAP / 2 + HASH_HDR + 4 + pad4z((size_t)L.P_pad / 32 + 1);  // hash kept, header, mbarrier
-    w += union_words(L, G);                                 // tile | scratch
+    w += union_words(L, G);                                 // per-tick scratch
     w += (size_t)(L.V_pad + 4);                             // vwin
-    w += kpad(L) * 10;                                      // per-player arrays
-    w += 64;                                                // oobx, ooby (bytes)
-    w += (size_t)(L.F_pad + 4);                             // freefood
-    w += 256;                                               // raster buffers
+    w += kpad(L) * 6 + (size_t)L.A_pad * 4;                 // per-player and per-agent arrays
+    w += 96;                                                // raster buffers
     w += 64;                                                // scalars + alive-list membership bits
     return w * 4 + 16;
 }
@@ -269,32 +291,30 @@ __device__ __forceinline__ Smem carve(float* base, const AgarLayout& L, int G) {
     s.hhdr = (int32_t*)p; p += HASH_HDR;                     // contiguous with the body: one bulk copy
     s.mbar = (uint64_t*)p; p += 4;
     s.isx = (int32_t*)p; p += pad4z((size_t)L.P_pad / 32 + 1);
-    s.tile = (uint32_t*)p;
     {
         int32_t* h = (int32_t*)p;
         s.hcur = h; h += HASH_BINS;
         s.pwin = (uint16_t*)h; h += L.P_pad / 2;
-        s.hits = (uint16_t*)h; h += L.P_pad / 2;
-        s.list = h; h += L.cells_total;
-        s.cnt = h; h += L.cells_total;
-        s.eater = h; h += L.cells_total;
+        s.hits = (uint16_t*)h; h += HITS_CAP / 2;
+        s.list = (uint16_t*)h; h += L.cells_total / 2;
+        s.eater = (uint16_t*)h; h += L.cells_total / 2;
+        s.cnt32 = (uint32_t*)h; h += L.cells_total / 2;
         s.gain = (float*)h;
     }
     p += union_words(L, G);
     s.vwin = (int32_t*)p; p += L.V_pad + 4;                  // V_pad % 4 == 0
     const size_t kp = kpad(L);
-    s.Tx = p; p += kp; s.Ty = p; p += kp; s.dirx = p; p += kp; s.diry = p; p += kp;
-    s.Cx = p; p += kp; s.Cy = p; p += kp; s.mass0 = p; p += kp;
-    s.pact = (int32_t*)p; p += kp; s.palive = (int32_t*)p; p += kp; s.pmask = (int32_t*)p; p += kp;
-    s.oobx = (uint8_t*)p; s.ooby = s.oobx + 128; p += 64;
-    s.freefood = (int32_t*)p; p += L.F_pad + 4;
-    s.rb = (int32_t*)p; p += 256;
+    s.Tx = p; p += kp; s.Ty = p; p += kp; s.Cx = p; p += kp; s.Cy = p; p += kp;
+    s.palive = (int32_t*)p; p += kp; s.pmask = (int32_t*)p; p += kp;
+    s.dirx = p; p += L.A_pad; s.diry = p; p += L.A_pad; s.mass0 = p; p += L.A_pad;
+    s.pact = (int32_t*)p; p += L.A_pad;
+    s.rb = (int32_t*)p; p += 96;
     s.sc = (int32_t*)p; p += 64;
     return s;
 }
 
 // -------------------------------------------------------------------------------- events
-__device__ __forceinline__ void ev_push_slow(int* counter, int32_t* events, int cap, int arena, int tick, int type, int x, int y) {
+__device__ __noinline__ void ev_push_slow(int* counter, int32_t* events, int cap, int arena, int tick, int type, int x, int y) {
     int i = atomicAdd(counter, 1);
     if (i < cap) *reinterpret_cast<int4*>(events + ((size_t)arena * cap + i) * 4) = make_int4(tick, type, x, y);
 }
@@ -310,7 +330,10 @@ __device__ __forceinline__ void clear_cell(const DevParams& p, const Smem& s, in
 }
 
 // env.reset() for one arena, in shared memory (reset_arena in the oracle)
-__device__ void reset_arena(const DevParams& p, const Smem& s, uint32_t gid_lo, uint32_t gid_hi) {
+// (out of line, re-deriving the shared-memory map itself: rare path, kept off the hot instruction stream)
+__device__ __noinline__ void reset_arena(const DevParams& p, uint32_t gid_lo, uint32_t gid_hi) {
+    extern __shared__ __align__(16) float smem_raw[];
+    const Smem s = carve(smem_raw, p.L, p.c.grid_size);
     const AgarLayout& L = p.L;
     const int tid = threadIdx.x, nt = blockDim.x;
     uint32_t tick = (uint32_t)s.reci[L.tick];
@@ -346,7 +369,10 @@ __device__ __forceinline__ int hash_coord(const DevParams& p, float v) {
 
 // counting sort of the present pellets into the HASH_W x HASH_W grid (all threads; ends synchronised).
 // Order inside a bin is arbitrary: every consumer reduces with min / integer counts.
-__device__ void build_hash(const DevParams& p, const Smem& s) {
+// Out of line: with the hash persisted across steps this runs only after resets and respawn overflows.
+__device__ __noinline__ void build_hash(const DevParams& p) {
+    extern __shared__ __align__(16) float smem_raw[];
+    const Smem s = carve(smem_raw, p.L, p.c.grid_size);
     const AgarLayout& L = p.L;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, P = p.c.num_pellets;
     const float* px = s.rec + L.pellet_x; const float* py = s.rec + L.pellet_y;
@@ -355,10 +381,9 @@ __device__ void build_hash(const DevParams& p, const Smem& s) {
     __syncthreads();
     for (int i = tid; i < P; i += nt) {
         const float x = px[i];
-        s.pwin[i] = NONE16;
         int b = 0xFFFF;
         if (x >= 0.0f) { b = hash_coord(p, py[i]) * HASH_W + hash_coord(p, x); atomicAdd(&s.hcur[b], 1); }
-        s.hits[i] = (uint16_t)b;  // bin cache for the scatter pass
+        s.pwin[i] = (uint16_t)b;  // bin cache for the scatter pass (which restores NONE16 == 0xFFFF)
     }
     __syncthreads();
     if (tid < 32) {
@@ -380,8 +405,8 @@ __device__ void build_hash(const DevParams& p, const Smem& s) {
     }
     __syncthreads();
     for (int i = tid; i < P; i += nt) {
-        const int b = s.hits[i];
-        if (b != 0xFFFF) s.sorted[atomicAdd(&s.hcur[b], 1)] = (uint16_t)i;
+        const int b = s.pwin[i];
+        if (b != 0xFFFF) { s.sorted[atomicAdd(&s.hcur[b], 1)] = (uint16_t)i; s.pwin[i] = NONE16; }
     }
     __syncthreads();
 }
@@ -404,27 +429,24 @@ __device__ __forceinline__ void build_list(const DevParams& p, const Smem& s) {
             int pos = 0;
             if (lane == 0) pos = atomicAdd(&s.sc[SC_NLIST], __popc(b));
             pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (al) s.list[pos + __popc(b & ((1u << lane) - 1u))] = g;
+            if (al) s.list[pos + __popc(b & ((1u << lane) - 1u))] = (uint16_t)g;
         }
     }
 }
 
-// count one entity in a bin of the packed 16-bit tile
-__device__ __forceinline__ void tile_inc(uint32_t* tile, int bin) { atomicAdd(&tile[bin >> 1], (bin & 1) ? 0x10000u : 1u); }
-__device__ __forceinline__ float4 tile_unpack(uint2 w) {
-    return make_float4((float)(w.x & 0xFFFFu), (float)(w.x >> 16), (float)(w.y & 0xFFFFu), (float)(w.y >> 16));
-}
-
 // features/extractors.py:77-78: grid index of an offset, int() truncation toward zero
+// (box is a power of two in every BASELINE config: the product is then exact and the IEEE division,
+// some 20 instructions plus a slow path at every site, is kept out of line)
+__device__ __noinline__ float div_rn(float a, float b) { return a / b; }
 __device__ __forceinline__ int grid_bin(const DevParams& p, float d, int half) {
-    return (int)(p.box_inv != 0.0f ? d * p.box_inv : d / p.box) + half;
+    return (int)(p.box_inv != 0.0f ? d * p.box_inv : div_rn(d, p.box)) + half;
 }
 
 // One warp: given up to 32 in-view cell entities (key = entity order, bin, mass; bin < 0 = none)
 // one per lane, leaves in `val` the sum of the masses of all entities sharing the lane's bin,
 // accumulated in ascending key order (bit-identical to the sequential `+=` of add_ones,
 // features/extractors.py:75-82) and returns true for the lane that holds the last entity of its bin.
-__device__ __forceinline__ bool ordered_bin_sums(int key, int bin, float m, int cnt, int lane, float& val) {
+__device__ __noinline__ float2 ordered_bin_sums_ool(int key, int bin, float m, int cnt, int lane) {
     int rank = 0;
     for (int i = 0; i < cnt; ++i) {
         int ki = __shfl_sync(0xffffffffu, key, i);
@@ -440,8 +462,31 @@ __device__ __forceinline__ bool ordered_bin_sums(int key, int bin, float m, int 
         if (br == bin && r <= rank) acc = acc + mr;
         if (br == bin && r > rank) later = true;
     }
-    val = acc;
-    return lane < cnt && bin >= 0 && !later;
+    return make_float2(acc, (lane < cnt && bin >= 0 && !later) ? 1.0f : 0.0f);
+}
+__device__ __forceinline__ bool ordered_bin_sums(int key, int bin, float m, int cnt, int lane, float& val) {
+    const float2 r = ordered_bin_sums_ool(key, bin, m, cnt, lane);  // all 32 lanes call together
+    val = r.x;
+    return r.y != 0.0f;
+}
+
+// features/extractors.py:84-96: the grid cell with index i on an axis is out of bounds when its world
+// corner (i - G//2)*box + c lies outside [0, arena)
+__device__ __forceinline__ bool oob_cell(const DevParams& p, int i, float c) {
+    const float w = p.oob_off[i] + c;
+    return !(0.0f <= w && w < p.c.arena_size);
+}
+
+// One count entity (value 1, add_ones with len(entity) <= 2) of an agent whose centroid is (cx, cy):
+// float adds of 1.0 are exact, so a global float reduction gives the reference's count in any order.
+// Cells that the sentinel pass overwrites afterwards (features/extractors.py:71-73) keep their -1.
+__device__ __forceinline__ void count_entity(const DevParams& p, float* __restrict__ chan, float x, float y, float cx,
+                                             float cy, int G, int half, float lim) {
+    const float dx = x - cx, dy = y - cy;
+    if (fabsf(dx) > lim || fabsf(dy) > lim) return;  // cannot land in the grid
+    const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
+    if (0 <= gx && gx < G && 0 <= gy && gy < G && !oob_cell(p, gx, cx) && !oob_cell(p, gy, cy))
+        atomicAdd(chan + gx * G + gy, 1.0f);
 }
 
 // GridFeatureExtractor.extract for every agent of the arena held in s.rec
@@ -449,35 +494,49 @@ __device__ __forceinline__ bool ordered_bin_sums(int key, int bin, float m, int 
 // use_hash: the pellet hash of this step is valid (pellets are then taken from the bins under
 // the view window plus the respawn list instead of scanning all of them).
 //
-// Count channels (pellets, viruses, foods) are binned into the shared-memory tile with exact
-// float atomics and streamed out with 128-bit stores.  Mass channels (own cells, others) hold a
-// handful of entities: the channel is stored as zeros / sentinels straight from registers and the
-// occupied bins are patched afterwards by warp 0 with sums taken in entity order.
+// Every channel of an agent is the same base image — zeros, with -1 in the out-of-bounds rows and
+// columns — plus a few occupied bins.  The base image goes out from registers with 128-bit
+// stores (one pass writes all channels; plain write-back stores, not streaming ones: the lines must
+// still be in L2 when their patches arrive or DRAM sees read-modify-writes); after a barrier the
+// occupied bins are patched: count
+// channels (pellets, viruses, foods) by float reductions of 1.0 in global memory, mass channels (own
+// cells, others) by warp 0 with sums taken in entity order.
 __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restrict__ obs_arena, bool use_hash) {
     const AgarLayout& L = p.L;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const int hbase = lane & 16, slot = lane & 15;
-    const int G = p.c.grid_size, GG = G * G, A = p.c.num_agents, K = p.K;
-    const float arena = p.c.arena_size, lim = p.raster_lim;
+    const int G = p.c.grid_size, GG = G * G, A = p.c.num_agents, K = p.K, C = p.C;
+    const float lim = p.raster_lim;
     const int half = G / 2;
     const float* px = s.rec + L.pellet_x; const float* py = s.rec + L.pellet_y;
     const float* cm = s.rec + L.cell_m; const float* cxs = s.rec + L.cell_x; const float* cys = s.rec + L.cell_y;
-    // raster buffers: others in view (unordered): key/bin/mass [32] each; patches: bin/value [2][32]
+    // other players' cells in view (unordered): key/bin/mass [32] each
     int* ob_key = s.rb; int* ob_bin = s.rb + 32; float* ob_m = (float*)(s.rb + 64);
-    int* pt_bin = s.rb + 96; float* pt_val = (float*)(s.rb + 160);  // [2*32] each: own cells then others
 
-    // the tile shares its memory with the per-tick scratch: clear it first
+    // channel numbers and which channels carry the sentinel
+    int ch_pel = -1, ch_cells = -1, ch_others = -1, ch_vir = -1, ch_food = -1, sentmask = 0;
     {
-        uint4* t4 = reinterpret_cast<uint4*>(s.tile);  // GG/2 words, GG % 16 == 0
-        for (int i = tid; i < GG / 8; i += nt) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+        int ch = 0;
+        if (p.c.obs_flags & AGAR_OBS_PELLETS) { ch_pel = ch; sentmask |= 1 << ch; ++ch; }
+        if (p.c.obs_flags & AGAR_OBS_CELLS) { ch_cells = ch; sentmask |= 1 << ch; ++ch; }
+        if (p.c.obs_flags & AGAR_OBS_OTHERS) { ch_others = ch; if (K > 1) sentmask |= 1 << ch; ++ch; }  // no pass without others
+        if (p.c.obs_flags & AGAR_OBS_VIRUSES) { ch_vir = ch; sentmask |= 1 << ch; ++ch; }
+        if (p.c.obs_flags & AGAR_OBS_FOODS) { ch_food = ch; sentmask |= 1 << ch; ++ch; }
     }
-    // centroids of all agents (half-warp per agent)
+    // centroids of all agents (half-warp per agent; single-cell agents take the one-term form)
     for (int base = (tid & ~31); base < A * MC; base += nt) {  // warp-uniform; warps without a valid lane skip
         const int g = base + lane;
         const bool valid = g < A * MC;
-        float cx = 0.0f, cy = 0.0f;
-        const bool has = hw_centroid(hbase, slot, valid ? cxs[g] : 0.0f, valid ? cys[g] : 0.0f, valid ? cm[g] : 0.0f, cx, cy);
-        if (valid && slot == 0) { s.Cx[g >> 4] = cx; s.Cy[g >> 4] = cy; s.palive[g >> 4] = has ? 1 : 0; }
+        const float m = valid ? cm[g] : 0.0f, x = valid ? cxs[g] : 0.0f, y = valid ? cys[g] : 0.0f;
+        const int n = __popc((__ballot_sync(FULL, m > 0.0f) >> hbase) & 0xFFFFu);
+        if (!__any_sync(FULL, n >= 2)) {
+            if (valid && n == 0 && slot == 0) s.palive[g >> 4] = 0;
+            if (m > 0.0f) { s.Cx[g >> 4] = (x * m) / m; s.Cy[g >> 4] = (y * m) / m; s.palive[g >> 4] = 1; }
+        } else {
+            float cx = 0.0f, cy = 0.0f;
+            const bool has = hw_centroid(hbase, slot, x, y, m, cx, cy);
+            if (valid && slot == 0) { s.Cx[g >> 4] = cx; s.Cy[g >> 4] = cy; s.palive[g >> 4] = has ? 1 : 0; }
+        }
     }
     if (tid == 0) s.sc[SC_NOB] = 0;
     // write-out geometry: when 4*nt is a multiple of G a thread keeps its 4 columns and walks rows
@@ -489,14 +548,9 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
     for (int a = 0; a < A; ++a) {
         const float cx = s.Cx[a], cy = s.Cy[a];
         const bool has = s.palive[a] != 0;
-        float* out_a = obs_arena + (size_t)a * p.C * GG;
-        // ---- gather phase: out-of-bounds flags, in-view cell entities ----
-        for (int i = tid; i < G; i += nt) {
-            float xl = p.oob_off[i] + cx, yl = p.oob_off[i] + cy;
-            s.oobx[i] = !(0.0f <= xl && xl < arena);
-            s.ooby[i] = !(0.0f <= yl && yl < arena);
-        }
-        if (has && (p.c.obs_flags & AGAR_OBS_OTHERS)) {
+        float* out_a = obs_arena + (size_t)a * C * GG;
+        // ---- gather: other players' cells in view ----
+        if (has && ch_others >= 0) {
             for (int g = tid; g < p.KC; g += nt) {
                 const float m = cm[g];
                 if (!(m > 0.0f) || (g >> 4) == a) continue;
@@ -509,53 +563,98 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                 }
             }
         }
-        __syncthreads();
-        const int nob = s.sc[SC_NOB];
-        const bool others_tile = nob > 32;  // more cells in view than one warp holds: sequential patch path
-        // ---- warp 0: ordered sums for the own-cells and others channels -> patch lists ----
-        if (tid < 32) {
-            pt_bin[lane] = -1; pt_bin[32 + lane] = -1;
-            if (has && (p.c.obs_flags & AGAR_OBS_CELLS)) {
-                const int g = a * MC + lane;
-                const float m = (lane < MC) ? cm[g] : 0.0f;
-                int bin = -1;
-                if (m > 0.0f) {
-                    const float dx = cxs[g] - cx, dy = cys[g] - cy;
-                    if (!(fabsf(dx) > lim || fabsf(dy) > lim)) {
-                        const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
-                        if (0 <= gx && gx < G && 0 <= gy && gy < G) bin = gx * G + gy;
+        // ---- base image of every channel ----
+        {
+            float4* out4 = reinterpret_cast<float4*>(out_a);
+            const int cstride = GG / 4;
+            const int smask = has ? sentmask : 0;  // an agent without cells observes zeros
+            if (fast) {
+                float4 row = zero4;
+                if (smask) {
+                    if (oob_cell(p, gy_t, cy)) row.x = -1.0f;
+                    if (oob_cell(p, gy_t + 1, cy)) row.y = -1.0f;
+                    if (oob_cell(p, gy_t + 2, cy)) row.z = -1.0f;
+                    if (oob_cell(p, gy_t + 3, cy)) row.w = -1.0f;
+                }
+                for (int i = tid, gx = gx_t; i < cstride; i += nt, gx += rstep) {
+                    const float4 v = (smask && oob_cell(p, gx, cx)) ? neg4 : row;
+                    for (int ch = 0; ch < C; ++ch) out4[ch * cstride + i] = ((smask >> ch) & 1) ? v : zero4;
+                }
+            } else {
+                for (int i = tid; i < cstride; i += nt) {
+                    float4 v = zero4;
+                    if (smask) {
+                        const int cell = i * 4, gx = cell / G, gy = cell - gx * G;
+                        if (oob_cell(p, gx, cx)) v = neg4;
+                        else {
+                            if (oob_cell(p, gy, cy)) v.x = -1.0f;
+                            if (oob_cell(p, gy + 1, cy)) v.y = -1.0f;
+                            if (oob_cell(p, gy + 2, cy)) v.z = -1.0f;
+                            if (oob_cell(p, gy + 3, cy)) v.w = -1.0f;
+                        }
                     }
+                    for (int ch = 0; ch < C; ++ch) out4[ch * cstride + i] = ((smask >> ch) & 1) ? v : zero4;
                 }
-                const unsigned inb = __ballot_sync(0xffffffffu, bin >= 0);
-                if (__popc(inb) == 1) {  // a single cell in view: 0 + m
-                    if (bin >= 0) { pt_bin[lane] = bin; pt_val[lane] = m; }
-                } else if (inb) {
-                    float val;
-                    if (ordered_bin_sums(lane, bin, m, MC, lane, val)) { pt_bin[lane] = bin; pt_val[lane] = val; }
-                }
-            }
-            if (has && (p.c.obs_flags & AGAR_OBS_OTHERS) && nob > 0 && !others_tile) {
-                const int key = lane < nob ? ob_key[lane] : NONE_I;
-                const int bin = lane < nob ? ob_bin[lane] : -1;
-                const float m = lane < nob ? ob_m[lane] : 0.0f;
-                float val = m;
-                if (nob == 1 ? lane == 0 : ordered_bin_sums(key, bin, m, nob, lane, val)) { pt_bin[32 + lane] = bin; pt_val[32 + lane] = val; }
             }
         }
-        // ---- channels ----
-        int ch = 0, ch_cells = -1, ch_others = -1;
-        for (int bit = 0; bit < 5; ++bit) {
-            const int flag = 1 << bit;
-            if (!(p.c.obs_flags & flag)) continue;
-            float4* out4 = reinterpret_cast<float4*>(out_a + (size_t)ch * GG);
-            bool sentinel = has;
-            if (flag == AGAR_OBS_OTHERS) sentinel = has && K > 1;
-            const bool mass = flag == AGAR_OBS_CELLS || flag == AGAR_OBS_OTHERS;
-            if (flag == AGAR_OBS_CELLS) ch_cells = ch;
-            if (flag == AGAR_OBS_OTHERS) ch_others = ch;
-            const bool via_tile = !mass;
-            if (via_tile && has) {
-                if (flag == AGAR_OBS_PELLETS && use_hash) {
+        __syncthreads();  // the base image is ordered before the patches; the gather list is complete
+        if (has) {
+            const int nob = s.sc[SC_NOB];
+            // ---- warp 0: own cells and others, sums in entity order, stored over the base image ----
+            if (tid < 32) {
+                if (ch_cells >= 0) {
+                    const int g = a * MC + lane;
+                    const float m = (lane < MC) ? cm[g] : 0.0f;
+                    int bin = -1;
+                    if (m > 0.0f) {
+                        const float dx = cxs[g] - cx, dy = cys[g] - cy;
+                        if (!(fabsf(dx) > lim || fabsf(dy) > lim)) {
+                            const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
+                            if (0 <= gx && gx < G && 0 <= gy && gy < G) bin = gx * G + gy;
+                        }
+                    }
+                    const unsigned inb = __ballot_sync(FULL, bin >= 0);
+                    float val = m;  // a single cell in view: 0 + m
+                    bool last = bin >= 0;
+                    if (__popc(inb) > 1) last = ordered_bin_sums(lane, bin, m, MC, lane, val);
+                    if (last) {
+                        const int gx = bin / G, gy = bin - gx * G;
+                        if (!(oob_cell(p, gx, cx) || oob_cell(p, gy, cy))) out_a[(size_t)ch_cells * GG + bin] = val;
+                    }
+                }
+                if (ch_others >= 0 && nob > 0 && nob <= 32) {
+                    const int key = lane < nob ? ob_key[lane] : NONE_I;
+                    const int bin = lane < nob ? ob_bin[lane] : -1;
+                    const float m = lane < nob ? ob_m[lane] : 0.0f;
+                    float val = m;
+                    bool last = lane == 0;
+                    if (nob > 1) last = ordered_bin_sums(key, bin, m, nob, lane, val);
+                    if (last) {
+                        const int gx = bin / G, gy = bin - gx * G;
+                        if (!(K > 1 && (oob_cell(p, gx, cx) || oob_cell(p, gy, cy)))) out_a[(size_t)ch_others * GG + bin] = val;
+                    }
+                }
+                if (ch_others >= 0 && nob > 32 && lane == 0) {
+                    // crowded view (more than 32 other cells inside it): one thread adds the masses in (player,
+                    // slot) order onto the zeros stored above — the same float sequence as the reference's `+=`
+                    float* outc = out_a + (size_t)ch_others * GG;
+                    for (int g = 0; g < p.KC; ++g) {
+                        const float m = cm[g];
+                        if (!(m > 0.0f) || (g >> 4) == a) continue;
+                        const float dx = cxs[g] - cx, dy = cys[g] - cy;
+                        if (fabsf(dx) > lim || fabsf(dy) > lim) continue;
+                        const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
+                        if (0 <= gx && gx < G && 0 <= gy && gy < G && !(K > 1 && (oob_cell(p, gx, cx) || oob_cell(p, gy, cy)))) {
+                            volatile float* q = outc + gx * G + gy;
+                            *q = *q + m;
+                        }
+                    }
+                }
+            }
+            // ---- count channels ----
+            if (ch_pel >= 0) {
+                float* chan = out_a + (size_t)ch_pel * GG;
+                if (use_hash) {
                     // pellets under the view window: hash rows (one warp per row), skipping entries that
                     // respawned since the hash was built; those come from the respawn list instead
                     const int bx0 = hash_coord(p, cx - lim), bx1 = hash_coord(p, cx + lim);
@@ -567,128 +666,111 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                             if ((s.isx[i >> 5] >> (i & 31)) & 1) continue;
                             const float x = px[i];
                             if (!(x >= 0.0f)) continue;
-                            const float dx = x - cx, dy = py[i] - cy;
-                            if (fabsf(dx) > lim || fabsf(dy) > lim) continue;
-                            const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
-                            if (0 <= gx && gx < G && 0 <= gy && gy < G) tile_inc(s.tile, gx * G + gy);
+                            count_entity(p, chan, x, py[i], cx, cy, G, half, lim);
                         }
                     }
                     const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
                     for (int e = tid; e < nex; e += nt) {
                         const int i = s.extras[e];
-                        const float dx = px[i] - cx, dy = py[i] - cy;
-                        if (fabsf(dx) > lim || fabsf(dy) > lim) continue;
-                        const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
-                        if (0 <= gx && gx < G && 0 <= gy && gy < G) tile_inc(s.tile, gx * G + gy);
-                    }
-                } else if (!mass) {
-                    // point entities: value 1 each (add_ones with len(entity) <= 2); float adds of 1.0
-                    // are exact, so shared-memory atomics give an order-independent count
-                    const float* ex; const float* ey; int n; bool marker;
-                    if (flag == AGAR_OBS_PELLETS) { ex = px; ey = py; n = p.c.num_pellets; marker = true; }
-                    else if (flag == AGAR_OBS_VIRUSES) { ex = s.rec + L.virus_x; ey = s.rec + L.virus_y; n = p.c.num_viruses; marker = false; }
-                    else { ex = s.rec + L.food_x; ey = s.rec + L.food_y; n = p.c.max_foods; marker = true; }
-                    for (int i = tid; i < n; i += nt) {
-                        float x = ex[i], y = ey[i];
-                        if (marker && !(x >= 0.0f)) continue;
-                        float dx = x - cx, dy = y - cy;
-                        if (fabsf(dx) > lim || fabsf(dy) > lim) continue;  // cannot land in the grid
-                        int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
-                        if (0 <= gx && gx < G && 0 <= gy && gy < G) tile_inc(s.tile, gx * G + gy);
-                    }
-                }
-            }
-            if (via_tile) {
-                __syncthreads();
-                // write the channel out with 128-bit streaming stores and re-zero the tile
-                uint2* tile2 = reinterpret_cast<uint2*>(s.tile);
-                const uint2 zero2 = make_uint2(0u, 0u);
-                if (!sentinel) {
-                    for (int i = tid; i < GG / 4; i += nt) { __stcs(out4 + i, tile_unpack(tile2[i])); tile2[i] = zero2; }
-                } else if (fast) {
-                    const bool o0 = s.ooby[gy_t], o1 = s.ooby[gy_t + 1], o2 = s.ooby[gy_t + 2], o3 = s.ooby[gy_t + 3];
-                    for (int i = tid, gx = gx_t; i < GG / 4; i += nt, gx += rstep) {
-                        float4 v = tile_unpack(tile2[i]);
-                        if (s.oobx[gx]) v = neg4;
-                        else { if (o0) v.x = -1.0f; if (o1) v.y = -1.0f; if (o2) v.z = -1.0f; if (o3) v.w = -1.0f; }
-                        __stcs(out4 + i, v);
-                        tile2[i] = zero2;
+                        count_entity(p, chan, px[i], py[i], cx, cy, G, half, lim);
                     }
                 } else {
-                    for (int i = tid; i < GG / 4; i += nt) {
-                        float4 v = tile_unpack(tile2[i]);
-                        int cell = i * 4, gx = cell / G, gy = cell - gx * G;
-                        if (s.oobx[gx]) v = neg4;
-                        else {
-                            if (s.ooby[gy]) v.x = -1.0f;
-                            if (s.ooby[gy + 1]) v.y = -1.0f;
-                            if (s.ooby[gy + 2]) v.z = -1.0f;
-                            if (s.ooby[gy + 3]) v.w = -1.0f;
-                        }
-                        __stcs(out4 + i, v);
-                        tile2[i] = zero2;
-                    }
-                }
-                __syncthreads();
-            } else {
-                // mass channel: zeros / sentinels straight from registers; occupied bins are patched below
-                if (!sentinel) {
-                    for (int i = tid; i < GG / 4; i += nt) __stcs(out4 + i, zero4);
-                } else if (fast) {
-                    float4 row = zero4;
-                    if (s.ooby[gy_t]) row.x = -1.0f;
-                    if (s.ooby[gy_t + 1]) row.y = -1.0f;
-                    if (s.ooby[gy_t + 2]) row.z = -1.0f;
-                    if (s.ooby[gy_t + 3]) row.w = -1.0f;
-                    for (int i = tid, gx = gx_t; i < GG / 4; i += nt, gx += rstep) __stcs(out4 + i, s.oobx[gx] ? neg4 : row);
-                } else {
-                    for (int i = tid; i < GG / 4; i += nt) {
-                        float4 v = zero4;
-                        int cell = i * 4, gx = cell / G, gy = cell - gx * G;
-                        if (s.oobx[gx]) v = neg4;
-                        else {
-                            if (s.ooby[gy]) v.x = -1.0f;
-                            if (s.ooby[gy + 1]) v.y = -1.0f;
-                            if (s.ooby[gy + 2]) v.z = -1.0f;
-                            if (s.ooby[gy + 3]) v.w = -1.0f;
-                        }
-                        __stcs(out4 + i, v);
+                    for (int i = tid; i < p.c.num_pellets; i += nt) {
+                        const float x = px[i];
+                        if (x >= 0.0f) count_entity(p, chan, x, py[i], cx, cy, G, half, lim);
                     }
                 }
             }
-            ++ch;
-        }
-        // ---- patches: the bulk stores above must be ordered before them ----
-        __syncthreads();
-        if (tid < 64 && has) {
-            const int which = tid >> 5;  // 0: own cells, 1: others
-            const int chn = which ? ch_others : ch_cells;
-            const int bin = pt_bin[tid];
-            if (chn >= 0 && bin >= 0 && !(which && others_tile)) {
-                const int gx = bin / G, gy = bin - gx * G;
-                const bool sent = which ? (K > 1) : true;
-                if (!(sent && (s.oobx[gx] || s.ooby[gy]))) out_a[(size_t)chn * GG + bin] = pt_val[tid];
+            if (ch_vir >= 0) {
+                float* chan = out_a + (size_t)ch_vir * GG;
+                const float* ex = s.rec + L.virus_x; const float* ey = s.rec + L.virus_y;
+                for (int i = tid; i < p.c.num_viruses; i += nt) count_entity(p, chan, ex[i], ey[i], cx, cy, G, half, lim);
             }
-        }
-        if (others_tile && has && ch_others >= 0 && tid == 0) {
-            // crowded view (more than 32 other cells inside it): one thread adds the masses in (player,
-            // slot) order onto the zeros stored above — the same float sequence as the reference's `+=`
-            float* outc = out_a + (size_t)ch_others * GG;
-            for (int g = 0; g < p.KC; ++g) {
-                const float m = cm[g];
-                if (!(m > 0.0f) || (g >> 4) == a) continue;
-                const float dx = cxs[g] - cx, dy = cys[g] - cy;
-                if (fabsf(dx) > lim || fabsf(dy) > lim) continue;
-                const int gx = grid_bin(p, dx, half), gy = grid_bin(p, dy, half);
-                if (0 <= gx && gx < G && 0 <= gy && gy < G && !(K > 1 && (s.oobx[gx] || s.ooby[gy]))) {
-                    volatile float* q = outc + gx * G + gy;
-                    *q = *q + m;
+            if (ch_food >= 0) {
+                float* chan = out_a + (size_t)ch_food * GG;
+                const float* ex = s.rec + L.food_x; const float* ey = s.rec + L.food_y;
+                for (int i = tid; i < p.c.max_foods; i += nt) {
+                    const float x = ex[i];
+                    if (x >= 0.0f) count_entity(p, chan, x, ey[i], cx, cy, G, half, lim);
                 }
             }
         }
-        if (tid == 0) s.sc[SC_NOB] = 0;
-        __syncthreads();
+        if (a + 1 < A) {  // the gather list and its counter are reused by the next agent
+            __syncthreads();
+            if (tid == 0) s.sc[SC_NOB] = 0;
+            __syncthreads();
+        }
     }
+}
+
+// Virus pops of one tick: a cell pops on the lowest virus it won; pops inside a
+// player are sequential in slot order.  All threads; ends synchronised.  Out of line: rare.
+__device__ __noinline__ void virus_pops(const DevParams& p, const KArgs& a, int arena, int tk, uint32_t tick,
+                                        uint32_t gid_lo, uint32_t gid_hi) {
+    extern __shared__ __align__(16) float smem_raw[];
+    const AgarLayout& L = p.L;
+    const AgarConfig& c = p.c;
+    const Smem s = carve(smem_raw, L, c.grid_size);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int K = p.K, V = c.num_viruses;
+    float* cx = s.rec + L.cell_x; float* cy = s.rec + L.cell_y; float* cix = s.rec + L.cell_ix;
+    float* ciy = s.rec + L.cell_iy; float* cm = s.rec + L.cell_m; float* ct = s.rec + L.cell_t;
+    float* vx = s.rec + L.virus_x; float* vy = s.rec + L.virus_y;
+    float* grec = a.state + (size_t)arena * L.words;
+    int32_t* inl = s.sc + 32;
+    const int n = s.sc[SC_NLIST];
+    for (int q = tid; q < n; q += nt) {
+        const int g = s.list[q];
+        s.eater[g] = NONE16;  // the speculative eat test is void: masses change below
+        if (!(cm[g] >= c.virus_pop_mass)) continue;
+        for (int v = 0; v < V; ++v)
+            if (s.vwin[v] == g) { s.eater[g] = (uint16_t)v; break; }   // eater[] doubles as "first virus won"
+    }
+    __syncthreads();
+    // one thread per player walks its slots in order (free slots are consumed sequentially
+    // inside a player, exactly as the oracle does)
+    for (int k = tid; k < K; k += nt) {
+#pragma unroll 1
+        for (int sl = 0; sl < MC; ++sl) {
+            const int g = k * MC + sl;
+            const int v = s.eater[g];
+            if (v == NONE16) continue;
+            s.eater[g] = NONE16;
+            float m1 = cm[g] + c.virus_mass;
+            int nfree = 0;
+#pragma unroll 1
+            for (int q = 0; q < MC; ++q) nfree += (cm[k * MC + q] == 0.0f) ? 1 : 0;
+            int np = nfree < c.pop_pieces ? nfree : c.pop_pieces;
+            ev_push(p, a, s, arena, tk, AGAR_EV_VIRUS_POP, g, v);
+            if (np > 0) {
+                const float DX[16] = AGAR_DIR16_X; const float DY[16] = AGAR_DIR16_Y;
+                float keep = m1 * 0.5f;
+                float piece = (m1 - keep) / (float)np;
+                cm[g] = keep; ct[g] = c.merge_delay;
+                const float gx = cx[g], gy = cy[g];
+                int q = 0;
+#pragma unroll 1
+                for (int j = 0; j < np; ++j) {
+                    while (cm[k * MC + q] != 0.0f) ++q;  // j-th free slot in ascending order
+                    int d = k * MC + q;
+                    cx[d] = gx; cy[d] = gy;
+                    cix[d] = DX[j] * c.pop_speed; ciy[d] = DY[j] * c.pop_speed;
+                    cm[d] = piece; ct[d] = c.merge_delay;
+                    ev_push(p, a, s, arena, tk, AGAR_EV_POP_PIECE, g, d);
+                    if (!(atomicOr(&inl[d >> 5], 1 << (d & 31)) & (1 << (d & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = (uint16_t)d;
+                }
+                s.sc[SC_MULTI] = 1;
+            } else {
+                cm[g] = m1;
+            }
+            float nx, ny;
+            rand_pos(p, gid_lo, gid_hi, (uint32_t)v, AGAR_STREAM_VIRUS_RESPAWN, tick, nx, ny);
+            vx[v] = nx; vy[v] = ny;
+            if (!(a.flags & F_READONLY)) { grec[L.virus_x + v] = nx; grec[L.virus_y + v] = ny; }
+        }
+    }
+    if (tid == 0) { s.sc[SC_ANYVHIT] = 0; s.sc[SC_ANYEAT] = 0; }
+    __syncthreads();
 }
 
 // --------------------------------------------------------------------------- the kernel
@@ -738,7 +820,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         if (load_hash) bulk_g2s(s.hstart, ghash, hash_bytes, s.mbar);
     }
     {   // meanwhile: clear the per-tick scratch
-        for (int i = tid; i < KC; i += nt) { s.cnt[i] = 0; s.eater[i] = NONE_I; s.gain[i] = 0.0f; }
+        for (int i = tid; i < KC / 2; i += nt) { s.cnt32[i] = 0u; reinterpret_cast<uint32_t*>(s.eater)[i] = 0xFFFFFFFFu; }
+        for (int i = tid; i < (int)gain_words(L); i += nt) s.gain[i] = 0.0f;
         if (tid < 64) s.sc[tid] = 0;
         if (a.flags & F_STEP) {
             for (int i = tid; i < L.P_pad / 2; i += nt) reinterpret_cast<uint32_t*>(s.pwin)[i] = 0xFFFFFFFFu;
@@ -753,7 +836,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
 
     bool static_dirty = false;  // whole record must be written back (after a reset)
     if (a.flags & F_RESET) {
-        if (!a.reset_mask || a.reset_mask[arena]) { reset_arena(p, s, gid_lo, gid_hi); static_dirty = true; }
+        if (!a.reset_mask || a.reset_mask[arena]) { reset_arena(p, gid_lo, gid_hi); static_dirty = true; }
     }
 
     if (a.flags & F_STEP) {
@@ -764,7 +847,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             if (tid < nex) { const int i = s.extras[tid]; atomicOr(&s.isx[i >> 5], 1 << (i & 31)); }
             if (tid == 0) { s.sc[SC_NEXTRAS] = nex; s.sc[SC_NEX0] = nex; s.sc[SC_HASHOK] = 1; }
         } else {
-            build_hash(p, s);
+            build_hash(p);
         }
         build_list(p, s);
         for (int base = 0; base < KC; base += nt) {  // membership bits of the list (one word per warp chunk)
@@ -783,10 +866,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 cx[g] = x; cy[g] = y; cm[g] = c.start_mass;  // the other fields of a dead player's slots are 0
                 ev_push(p, a, s, arena, 0, AGAR_EV_RESPAWN, k, 0);
                 pm = 1u; s.pmask[k] = 1;
-                if (!(atomicOr(&inl[g >> 5], 1 << (g & 31)) & (1 << (g & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = g;
+                if (!(atomicOr(&inl[g >> 5], 1 << (g & 31)) & (1 << (g & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = (uint16_t)g;
             }
             s.palive[k] = pm != 0u;
-            s.pact[k] = 0; s.Tx[k] = 0.0f; s.Ty[k] = 0.0f; s.dirx[k] = 1.0f; s.diry[k] = 0.0f;
+            s.Tx[k] = 0.0f; s.Ty[k] = 0.0f;
+            if (k < A) { s.pact[k] = 0; s.dirx[k] = 1.0f; s.diry[k] = 0.0f; }
             float Cx = 0.0f, Cy = 0.0f, mb = 0.0f;
             if (__popc(pm) == 1) {  // np.average over one cell: (x*m)/m, exactly as the general path gives
                 const int g = k * MC + __ffs(pm) - 1;
@@ -925,18 +1009,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     cm[d] = halfm; ct[d] = c.merge_delay;
                     ev_push(p, a, s, arena, 0, AGAR_EV_SPLIT, g, d);
                     s.sc[SC_MULTI] = 1;
-                    if (!(atomicOr(&inl[d >> 5], 1 << (d & 31)) & (1 << (d & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = d;
+                    if (!(atomicOr(&inl[d >> 5], 1 << (d & 31)) & (1 << (d & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = (uint16_t)d;
                 }
             }
         }
         // ---- feed: cells in gid order take free food slots in ascending order (warp 0) ----
         if (s.sc[SC_ANYFEED] && tid < 32) {
+            int32_t* freefood = reinterpret_cast<int32_t*>(s.gain);  // gain[] rests at 0 outside the eat phase: borrowed
             int nfree = 0;
             for (int base = 0; base < L.F_pad; base += 32) {
                 int f = base + lane;
                 bool fr = f < F && !(fx[f] >= 0.0f);
                 unsigned b = __ballot_sync(0xffffffffu, fr);
-                if (fr) s.freefood[nfree + __popc(b & ((1u << lane) - 1u))] = f;
+                if (fr) freefood[nfree + __popc(b & ((1u << lane) - 1u))] = f;
                 nfree += __popc(b);
             }
             __syncwarp();
@@ -949,7 +1034,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 unsigned b = __ballot_sync(0xffffffffu, elig);
                 int rank = used + __popc(b & ((1u << lane) - 1u));
                 if (elig && rank < nfree) {
-                    int f = s.freefood[rank];
+                    int f = freefood[rank];
                     float r = sqrtf(m * r2pm);
                     cm[g] = m - c.food_mass;
                     float off = r + c.food_spawn_gap;
@@ -960,12 +1045,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 }
                 used += __popc(b);
             }
+            __syncwarp();
+            for (int e = lane; e < nfree; e += 32) s.gain[e] = 0.0f;  // hand gain[] back zeroed
         }
         __syncthreads();
 
         for (int tk = 0; tk < c.ticks_per_step; ++tk) {
             const uint32_t tick = tick0 + (uint32_t)tk;
-            if (s.sc[SC_REBUILD]) build_hash(p, s);  // too many respawns since the last build (uniform)
+            if (s.sc[SC_REBUILD]) build_hash(p);  // too many respawns since the last build (uniform)
             // ---- motion + pellet query: four lanes per alive cell.  All four evaluate the motion (lane 0
             //      stores it) and then share the scan of the hash runs under the cell's padded bounding
             //      box and of the respawn list.  A pellet whose centre lies inside the disc is claimed
@@ -1009,14 +1096,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                             if (!(qx >= 0.0f)) continue;
                             const float ex = qx - x, ey = py[i] - y;
                             if (ex * ex + ey * ey < r2)
-                                if (claim_min16(&s.pwin[i], g)) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
+                                if (claim_min16(&s.pwin[i], g)) { const int e = atomicAdd(&s.sc[SC_NHITS], 1); if (e < HITS_CAP) s.hits[e] = (uint16_t)i; }
                         }
                     }
                     for (int e = l4; e < nex; e += 4) {  // respawned since the hash was built (a stale hash
                         const int i = s.extras[e];       // entry of the same pellet may claim twice: atomicMin dedups)
                         const float ex = px[i] - x, ey = py[i] - y;
                         if (ex * ex + ey * ey < r2)
-                            if (claim_min16(&s.pwin[i], g)) s.hits[atomicAdd(&s.sc[SC_NHITS], 1)] = (uint16_t)i;
+                            if (claim_min16(&s.pwin[i], g)) { const int e = atomicAdd(&s.sc[SC_NHITS], 1); if (e < HITS_CAP) s.hits[e] = (uint16_t)i; }
                     }
                 }
 #pragma unroll 1
@@ -1030,11 +1117,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             const bool gains = nh > 0 || food_any;        // some mass changes this tick before the eat test
             // ---- resolve the claimed pellets: winner = lowest gid (atomicMin), respawn by Philox ----
             if (nh > 0) {
-                for (int h = tid; h < nh; h += nt) {
-                    const int i = s.hits[h];
+                const bool listed = nh <= HITS_CAP;  // else the list overflowed: every pellet's winner slot is examined
+                const int nscan = listed ? nh : c.num_pellets;
+                for (int h = tid; h < nscan; h += nt) {
+                    const int i = listed ? (int)s.hits[h] : h;
                     const int g = s.pwin[i];
+                    if (g == NONE16) continue;
                     s.pwin[i] = NONE16;
-                    atomicAdd(&s.cnt[g], 1);
+                    cnt_inc(s.cnt32, g);
                     ev_push(p, a, s, arena, tk, AGAR_EV_PELLET_EATEN, g, i);
                     float nx = -1.0f, ny = -1.0f;
                     if (c.pellet_regen) {
@@ -1054,8 +1144,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 const int n = s.sc[SC_NLIST];
                 for (int q = tid; q < n; q += nt) {
                     const int g = s.list[q];
-                    const int e = s.cnt[g];
-                    if (e) { cm[g] = cm[g] + (float)e * c.pellet_mass; s.cnt[g] = 0; }
+                    const int e = cnt_get(s.cnt32, g);
+                    if (e) { cm[g] = cm[g] + (float)e * c.pellet_mass; cnt_clear(s.cnt32, g); }
                 }
                 __syncthreads();
                 for (int f = tid; f < F; f += nt) {
@@ -1074,7 +1164,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                         if (m > 0.0f && dx * dx + dy * dy < m * r2pm && g < best) best = g;
                     }
                     if (best != NONE_I) {
-                        atomicAdd(&s.cnt[best], 1);
+                        cnt_inc(s.cnt32, best);
                         ev_push(p, a, s, arena, tk, AGAR_EV_FOOD_EATEN, best, f);
                         fx[f] = -1.0f; fy[f] = 0.0f; fvx[f] = 0.0f; fvy[f] = 0.0f;
                     }
@@ -1105,7 +1195,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     }
                     best = min(best, __shfl_xor_sync(FULL, best, 1));
                     best = min(best, __shfl_xor_sync(FULL, best, 2));
-                    if (l4 == 0 && best != NONE_I) { s.eater[j] = best; s.sc[SC_ANYEAT] = 1; }
+                    if (l4 == 0 && best != NONE_I) { s.eater[j] = (uint16_t)best; s.sc[SC_ANYEAT] = 1; }
                 }
             };
             // ---- apply gains (pellets, or foods when present); heavy cells claim viruses.  On a tick
@@ -1116,8 +1206,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 for (int q = tid; q < n; q += nt) {
                     const int g = s.list[q];
                     float m = cm[g];
-                    const int e = s.cnt[g];
-                    if (e) { m = m + (float)e * unit; cm[g] = m; s.cnt[g] = 0; }
+                    const int e = cnt_get(s.cnt32, g);
+                    if (e) { m = m + (float)e * unit; cm[g] = m; cnt_clear(s.cnt32, g); }
                     if (V > 0 && m >= c.virus_pop_mass) {
                         const float r2 = m * r2pm, x = cx[g], y = cy[g];
                         for (int v = 0; v < V; ++v) {
@@ -1128,74 +1218,26 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 }
             }
             if (tid == 0 && gains) { s.sc[SC_NHITS] = 0; s.sc[SC_FOODANY] = 0; }  // a barrier follows whenever gains
-            if (K > 1 && !gains) eat_test();
-            if (gains || V > 0 || K > 1) __syncthreads();
-            bool eat_done = K > 1 && !gains;
-            // ---- virus pops ----
-            if (V > 0 && s.sc[SC_ANYVHIT]) {  // block-uniform, rare
-                const int n = s.sc[SC_NLIST];
-                for (int q = tid; q < n; q += nt) {
-                    const int g = s.list[q];
-                    if (eat_done) s.eater[g] = NONE_I;  // the speculative eat test is void: masses change below
-                    if (!(cm[g] >= c.virus_pop_mass)) continue;
-                    for (int v = 0; v < V; ++v)
-                        if (s.vwin[v] == g) { s.eater[g] = v; break; }   // eater[] doubles as "first virus won"
+            if (gains && K > 1) __syncthreads();  // the eat test reads the updated masses
+            // ---- cell eats cell (one code site).  It runs speculatively before the virus pops are known; a
+            //      pop (rare) changes masses, voids the result and the test is taken again ----
+            for (bool again = true; again;) {
+                if (K > 1) eat_test();
+                if (gains || V > 0 || K > 1) __syncthreads();
+                again = false;
+                if (V > 0 && s.sc[SC_ANYVHIT]) {  // block-uniform, rare: out of line
+                    virus_pops(p, a, arena, tk, tick, gid_lo, gid_hi);
+                    again = K > 1;
                 }
-                __syncthreads();
-                // one thread per player walks its slots in order (free slots are consumed sequentially
-                // inside a player, exactly as the oracle does)
-                for (int k = tid; k < K; k += nt) {
-#pragma unroll 1
-                    for (int sl = 0; sl < MC; ++sl) {
-                        const int g = k * MC + sl;
-                        const int v = s.eater[g];
-                        if (v == NONE_I) continue;
-                        s.eater[g] = NONE_I;
-                        float m1 = cm[g] + c.virus_mass;
-                        int freeslot[MC]; int nfree = 0;
-#pragma unroll 1
-                        for (int q = 0; q < MC; ++q)
-                            if (cm[k * MC + q] == 0.0f) freeslot[nfree++] = q;
-                        int np = nfree < c.pop_pieces ? nfree : c.pop_pieces;
-                        ev_push(p, a, s, arena, tk, AGAR_EV_VIRUS_POP, g, v);
-                        if (np > 0) {
-                            const float DX[16] = AGAR_DIR16_X; const float DY[16] = AGAR_DIR16_Y;
-                            float keep = m1 * 0.5f;
-                            float piece = (m1 - keep) / (float)np;
-                            cm[g] = keep; ct[g] = c.merge_delay;
-#pragma unroll 1
-                            for (int j = 0; j < np; ++j) {
-                                int d = k * MC + freeslot[j];
-                                cx[d] = cx[g]; cy[d] = cy[g];
-                                cix[d] = DX[j] * c.pop_speed; ciy[d] = DY[j] * c.pop_speed;
-                                cm[d] = piece; ct[d] = c.merge_delay;
-                                ev_push(p, a, s, arena, tk, AGAR_EV_POP_PIECE, g, d);
-                                if (!(atomicOr(&inl[d >> 5], 1 << (d & 31)) & (1 << (d & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = d;
-                            }
-                            s.sc[SC_MULTI] = 1;
-                        } else {
-                            cm[g] = m1;
-                        }
-                        float nx, ny;
-                        rand_pos(p, gid_lo, gid_hi, (uint32_t)v, AGAR_STREAM_VIRUS_RESPAWN, tick, nx, ny);
-                        vx[v] = nx; vy[v] = ny;
-                        if (!(a.flags & F_READONLY)) { grec[L.virus_x + v] = nx; grec[L.virus_y + v] = ny; }
-                    }
-                }
-                if (tid == 0) { s.sc[SC_ANYVHIT] = 0; s.sc[SC_ANYEAT] = 0; }
-                eat_done = false;
-                __syncthreads();
             }
-            // ---- cell eats cell ----
             if (K > 1) {
-                if (!eat_done) { eat_test(); __syncthreads(); }
                 if (s.sc[SC_ANYEAT]) {
                     const int n = s.sc[SC_NLIST];
                     if (tid < 32) {  // gains added in ascending prey order (float sum order is part of the spec)
                         for (int base = 0; base < KC; base += 32) {
                             int j = base + lane;
-                            int w = (j < KC) ? s.eater[j] : NONE_I;
-                            unsigned mask = __ballot_sync(0xffffffffu, w != NONE_I);
+                            int w = (j < KC) ? (int)s.eater[j] : NONE16;
+                            unsigned mask = __ballot_sync(0xffffffffu, w != NONE16);
                             while (mask) {
                                 int src = __ffs(mask) - 1;
                                 if (lane == src) {
@@ -1210,7 +1252,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     __syncthreads();
                     for (int q = tid; q < n; q += nt) {
                         const int g = s.list[q];
-                        if (s.eater[g] != NONE_I) { clear_cell(p, s, g); s.eater[g] = NONE_I; }  // eaten: forfeits its gains
+                        if (s.eater[g] != NONE16) { clear_cell(p, s, g); s.eater[g] = NONE16; }  // eaten: forfeits its gains
                         else if (s.gain[g] > 0.0f) cm[g] = cm[g] + s.gain[g];
                         s.gain[g] = 0.0f;
                     }
@@ -1288,7 +1330,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         }
         __syncthreads();
         if (c.auto_reset && !s.sc[SC_ALLDONE]) {
-            reset_arena(p, s, gid_lo, gid_hi); static_dirty = true;
+            reset_arena(p, gid_lo, gid_hi); static_dirty = true;
             if (tid == 0) s.sc[SC_HASHOK] = 0;  // pellets were redrawn: the raster scans them all
         }
         // ---- persist the pellet hash for the next step ----
@@ -1322,7 +1364,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     }
     // ---- observations ----
     if ((a.flags & F_OBS) && a.obs) {
-        __syncthreads();  // the tile shares memory with the pellet hash
+        __syncthreads();
         const int GG = c.grid_size * c.grid_size;
         raster_arena(p, s, a.obs + (size_t)arena * A * p.C * GG, s.sc[SC_HASHOK] != 0 && s.sc[SC_REBUILD] == 0);
     }

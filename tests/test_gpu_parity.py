@@ -120,6 +120,17 @@ def test_dense_small_arena_all_event_types(oracle):
     genv.close()
 
 
+def test_more_pellets_eaten_in_a_tick_than_the_hit_list_holds(oracle):
+    """A huge cell over a carpet of pellets eats hundreds of them per tick: the kernel's per-tick hit list
+    (128 entries) overflows and the resolver falls back to scanning every pellet's winner slot."""
+    genv, oenv = make_pair(oracle, seed=11, num_arenas=4, num_agents=2, num_bots=1, num_pellets=1500, arena_size=60.0,
+                           view_size=64.0, grid_size=32, obs_flags=7, event_capacity=8192, start_mass=2500.0,
+                           split_min_mass=1e9, virus_pop_mass=1e9)
+    counts = lockstep(genv, oenv, 12, np.random.default_rng(5), acts=(0,), p_act=0.0)
+    assert counts[1] > 4 * 12 * 4 * 128, counts  # well over 128 pellets per arena-tick on average
+    genv.close()
+
+
 def test_cfg4_sixteen_agents_split_merge(oracle):
     """BASELINE configs[3] world: 16 agents per arena with split/merge (ppo.textproto:4-23)."""
     genv, oenv = make_pair(oracle, seed=4, num_arenas=3, num_agents=16, event_capacity=512, obs_flags=7,
