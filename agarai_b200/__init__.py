@@ -8,6 +8,7 @@ without a CUDA device raises (there is no CPU fallback).
 from ._lib import AgarConfig, AgarError, AgarLayout, default_config
 from .actions import ActionConfig, ActionConverter, action_size, ppo_action_table, unravel_action_table
 from .env import BatchedAgarioEnv, GymCompatEnv, config_from_gym_kwargs, make
+from .features import FeatureExtractor, GridFeatureExtractor, ScreenFeatureExtractor
 from .gae import gae, gae_and_returns, make_returns
 from .rollout import DeviceRollout
 
@@ -15,4 +16,5 @@ __all__ = [
     "AgarConfig", "AgarError", "AgarLayout", "default_config", "ActionConfig", "ActionConverter",
     "action_size", "ppo_action_table", "unravel_action_table", "BatchedAgarioEnv", "GymCompatEnv",
     "config_from_gym_kwargs", "make", "gae", "gae_and_returns", "make_returns", "DeviceRollout",
+    "FeatureExtractor", "GridFeatureExtractor", "ScreenFeatureExtractor",
 ]

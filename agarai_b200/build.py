@@ -8,6 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = [os.path.join(_HERE, "csrc", "agar_b200.cu")]
 DEPS = SOURCES + [
     os.path.join(_HERE, "csrc", "agar_kernels.cuh"),
+    os.path.join(_HERE, "csrc", "agar_features.cuh"),
     os.path.join(_HERE, "..", "include", "agar_b200.h"),
     os.path.join(_HERE, "..", "include", "agar_spec.h"),
 ]

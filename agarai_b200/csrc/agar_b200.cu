@@ -12,6 +12,7 @@
 #include "../../include/agar_b200.h"
 #include "../../include/agar_spec.h"
 #include "agar_kernels.cuh"
+#include "agar_features.cuh"
 
 using namespace agar;
 
@@ -337,6 +338,47 @@ int agar_gae(const float* d_reward, const float* d_value, const uint8_t* d_done,
     const int threads = 128, blocks = (N + threads - 1) / threads;
     agar_gae_kernel<8><<<blocks, threads, 0, (cudaStream_t)stream>>>(d_reward, d_value, d_done, d_end_value, g, cgl,
                                                                   d_adv, d_ret, T, N);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agar_ram_feature_size(int32_t n_pellet, int32_t n_virus, int32_t n_food, int32_t n_other, int32_t n_cell) {
+    if (n_pellet < 0 || n_virus < 0 || n_food < 0 || n_other < 0 || n_cell < 0) return -1;
+    return 2 * (n_pellet + n_virus + n_food) + 5 * (1 + n_other) * n_cell;
+}
+
+int agar_observe_ram(AgarEnv* e, int32_t n_pellet, int32_t n_virus, int32_t n_food, int32_t n_other, int32_t n_cell,
+                     float* d_out, void* stream) {
+    if (!e || !d_out) return fail("NULL argument");
+    const int size = agar_ram_feature_size(n_pellet, n_virus, n_food, n_other, n_cell);
+    if (size <= 0) return fail("agar_observe_ram: bad feature counts");
+    if (n_cell > AGAR_MAX_CELLS) return fail("agar_observe_ram: n_cell exceeds the 16 cell slots of a player");
+    CUDA_OK(cudaSetDevice(e->device));
+    RamParams rp;
+    rp.n_pellet = n_pellet; rp.n_virus = n_virus; rp.n_food = n_food; rp.n_other = n_other; rp.n_cell = n_cell;
+    rp.size = size; rp.filler = -1000.0f;
+    const AgarConfig& c = e->p.c;
+    int most = c.num_pellets > c.num_viruses ? c.num_pellets : c.num_viruses;
+    if (c.max_foods > most) most = c.max_foods;
+    rp.sort_cap = 1;
+    while (rp.sort_cap < most) rp.sort_cap <<= 1;
+    const size_t smem = (size_t)(rp.sort_cap + 64) * sizeof(unsigned long long);
+    CUDA_OK(cudaFuncSetAttribute(ram_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ram_features_kernel<<<c.num_arenas * c.num_agents, 128, smem, (cudaStream_t)stream>>>(e->p, rp, e->d_state, d_out);
+    CUDA_OK(cudaGetLastError());
+    e->launches += 1;
+    return 0;
+}
+
+int agar_screen_gray(const uint8_t* d_rgb, int64_t n_pixels, void* d_out, int32_t out_f64, void* stream) {
+    if (n_pixels < 0) return fail("agar_screen_gray: negative size");
+    if (n_pixels == 0) return 0;
+    if (!d_rgb || !d_out) return fail("NULL argument");
+    if (((uintptr_t)d_rgb & 15) != 0 || ((uintptr_t)d_out & 15) != 0) return fail("agar_screen_gray: buffers must be 16-byte aligned");
+    const long long threads = (n_pixels + 15) / 16;
+    const unsigned blocks = (unsigned)((threads + 255) / 256);
+    if (out_f64) screen_gray_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_rgb, (long long)n_pixels, (double*)d_out);
+    else screen_gray_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_rgb, (long long)n_pixels, (float*)d_out);
     CUDA_OK(cudaGetLastError());
     return 0;
 }

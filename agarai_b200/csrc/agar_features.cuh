@@ -1,0 +1,223 @@
+// agar_features.cuh — the other two observation families of features/extractors.py on the device:
+//
+//   screen_gray_kernel   ScreenFeatureExtractor.extract (features/extractors.py:152-164): mean over the
+//                        trailing colour axis of uint8 frames.  HBM-bound: 3 B read, 4 or 8 B written per pixel.
+//   ram_features_kernel  FeatureExtractor.extract (features/extractors.py:99-149 with the helpers :171-212):
+//                        nearest-k pellets / viruses / foods, the agent's cells, the closest players' cells,
+//                        as one fixed-length vector per agent, straight from the arena records.
+//
+// Both are bit-exact restatements in float32/float64 single IEEE operations (compiled with -fmad=false); the
+// sequential definitions are oracle_screen_gray / oracle_ram_extract in oracle/agar_oracle.c.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "agar_kernels.cuh"
+
+namespace agar {
+
+// ------------------------------------------------------------------------------ screen -> gray
+// numpy: observation.mean(axis=-1) on uint8 adds the three bytes in float64 and divides by 3.0; the sum of
+// three bytes is exact in any order, so out = (double)(r+g+b) / 3.0 is the same float64 (float32 output is that
+// value rounded once, i.e. what `.astype(np.float32)` of the reference's result gives).
+// One thread converts 16 pixels: three 128-bit loads, four 128-bit (or eight) stores.
+template <typename OutT>
+__global__ void __launch_bounds__(256) screen_gray_kernel(const uint8_t* __restrict__ rgb, long long n_pixels,
+                                                          OutT* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p0 = t * 16;
+    if (p0 >= n_pixels) return;
+    if (p0 + 16 <= n_pixels) {
+        const uint4* src = reinterpret_cast<const uint4*>(rgb + p0 * 3);  // 48 B per thread: 16 B aligned when rgb is
+        uint4 w[3];
+        w[0] = __ldcs(src); w[1] = __ldcs(src + 1); w[2] = __ldcs(src + 2);
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(w);
+        OutT v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (OutT)((double)((int)b[3 * i] + (int)b[3 * i + 1] + (int)b[3 * i + 2]) / 3.0);
+        if (sizeof(OutT) == 4) {
+            float4* o = reinterpret_cast<float4*>(out + p0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) __stcs(o + i, make_float4((float)v[4 * i], (float)v[4 * i + 1], (float)v[4 * i + 2], (float)v[4 * i + 3]));
+        } else {
+            double2* o = reinterpret_cast<double2*>(out + p0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) __stcs(o + i, make_double2((double)v[2 * i], (double)v[2 * i + 1]));
+        }
+    } else {
+        for (long long p = p0; p < n_pixels; ++p)
+            out[p] = (OutT)((double)((int)rgb[3 * p] + (int)rgb[3 * p + 1] + (int)rgb[3 * p + 2]) / 3.0);
+    }
+}
+
+// ------------------------------------------------------------------------------ RAM-style features
+struct RamParams {
+    int n_pellet, n_virus, n_food, n_other, n_cell;  // FeatureExtractor.__init__ (features/extractors.py:101-106)
+    int size;                                         // 2*(n_pellet+n_virus+n_food) + 5*(1+n_other)*n_cell (:108)
+    int sort_cap;                                     // power of two >= max(P, V, F): shared-memory sort buffer
+    float filler;                                     // -1000 (:110)
+};
+
+// ascending bitonic sort of n (power of two) 64-bit keys in shared memory, all threads of the CTA
+__device__ __forceinline__ void bitonic_sort_u64(unsigned long long* key, int n) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n; i += nt) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = key[i], b = key[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { key[i] = b; key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// get_entity_features(loc, entities[:, :2], n) for point entities (features/extractors.py:171-180,
+// :197-204): the n entities nearest to loc by float32 sqrt(dx*dx + dy*dy), ties by index (the stable order;
+// numpy's default argsort leaves ties unspecified), as positions relative to loc; zero rows pad.
+// key = distance bits (non-negative floats order like their bit patterns) << 32 | index.
+__device__ void ram_nearest_points(unsigned long long* key, int cap, const float* ex, const float* ey, int count,
+                                   bool marker, float lx, float ly, int n, float* __restrict__ out) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int m = 1;
+    while (m < count) m <<= 1;
+    if (m > cap) m = cap;
+    for (int i = tid; i < m; i += nt) {
+        unsigned long long k = ~0ull;
+        if (i < count) {
+            const float x = ex[i];
+            if (!marker || x >= 0.0f) {
+                const float dx = x - lx, dy = ey[i] - ly;
+                const float d = sqrtf(dx * dx + dy * dy);
+                k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
+            }
+        }
+        key[i] = k;
+    }
+    __syncthreads();
+    bitonic_sort_u64(key, m);
+    for (int r = tid; r < n; r += nt) {
+        float ox = 0.0f, oy = 0.0f;
+        if (r < m && key[r] != ~0ull) {
+            const int i = (int)(unsigned)key[r];
+            ox = ex[i] - lx; oy = ey[i] - ly;
+        }
+        out[2 * r] = ox; out[2 * r + 1] = oy;
+    }
+    __syncthreads();
+}
+
+// One warp: largest_cells(player, n) then get_entity_features(loc, cells, n, relative) for one player's 16
+// cell slots (lane = slot; lanes >= 16 idle).  features/extractors.py:182-184 sorts ASCENDING by mass and keeps
+// the first n (so it keeps the n smallest: reference quirk, reproduced), :197-200 then orders those by distance
+// to loc.  Both sorts are stable here (ties keep the earlier order).  Rows are [x, y, ix, iy, mass] (the
+// columns 2-3 the reference never interprets carry the cell's launch impulse).  Zero rows pad.
+__device__ void ram_player_cells(const float* cx, const float* cy, const float* cix, const float* ciy, const float* cm,
+                                 float lx, float ly, bool relative, int n, float* __restrict__ out, int lane) {
+    const bool in = lane < MC;
+    const float m = in ? cm[lane] : 0.0f;
+    const float x = in ? cx[lane] : 0.0f, y = in ? cy[lane] : 0.0f;
+    const bool alive = m > 0.0f;
+    // rank by (mass, slot) among alive cells
+    int rank_m = 0;
+    for (int j = 0; j < MC; ++j) {
+        const float mj = __shfl_sync(FULL, m, j);
+        if (mj > 0.0f && (mj < m || (mj == m && j < lane))) ++rank_m;
+    }
+    const bool sel = alive && rank_m < n;
+    const float dx = x - lx, dy = y - ly;
+    const float d = sqrtf(dx * dx + dy * dy);
+    // rank by (distance, mass rank) among the selected
+    int rank_d = 0;
+    for (int j = 0; j < MC; ++j) {
+        const float dj = __shfl_sync(FULL, d, j);
+        const int rj = __shfl_sync(FULL, rank_m, j);
+        const bool sj = __shfl_sync(FULL, sel ? 1 : 0, j) != 0;
+        if (sj && (dj < d || (dj == d && rj < rank_m))) ++rank_d;
+    }
+    const int nsel = __popc(__ballot_sync(FULL, sel));
+    if (sel) {
+        float* o = out + 5 * rank_d;
+        o[0] = relative ? dx : x; o[1] = relative ? dy : y;
+        o[2] = cix[lane]; o[3] = ciy[lane]; o[4] = m;
+    }
+    for (int r = nsel * 5 + lane; r < n * 5; r += 32) out[r] = 0.0f;
+}
+
+// grid = (arenas * agents); block = 128; dynamic smem = sort_cap * 8 + 64 * 8 bytes.
+__global__ void __launch_bounds__(128) ram_features_kernel(const __grid_constant__ DevParams p, const __grid_constant__ RamParams rp,
+                                                           const float* __restrict__ state, float* __restrict__ out_all) {
+    extern __shared__ __align__(16) unsigned long long ram_smem[];
+    unsigned long long* key = ram_smem;              // [sort_cap]
+    unsigned long long* pkey = ram_smem + rp.sort_cap;  // [64] other players by distance
+    __shared__ float s_loc[2];
+    __shared__ int s_has;
+    const AgarLayout& L = p.L;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int A = p.c.num_agents, K = p.K;
+    const int arena = blockIdx.x / A, a = blockIdx.x - arena * A;
+    const float* rec = state + (size_t)arena * L.words;
+    float* out = out_all + (size_t)blockIdx.x * rp.size;
+    const float* cx = rec + L.cell_x; const float* cy = rec + L.cell_y; const float* cix = rec + L.cell_ix;
+    const float* ciy = rec + L.cell_iy; const float* cm = rec + L.cell_m;
+
+    // loc = position(agent) (features/extractors.py:207-212)
+    if (warp == 0) {
+        const int g = a * MC + (lane & 15);
+        const bool v = lane < MC;
+        float lx = 0.0f, ly = 0.0f;
+        const bool has = hw_centroid(0, lane & 15, v ? cx[g] : 0.0f, v ? cy[g] : 0.0f, v ? cm[g] : 0.0f, lx, ly);
+        if (lane == 0) { s_loc[0] = lx; s_loc[1] = ly; s_has = has ? 1 : 0; }
+    }
+    __syncthreads();
+    if (!s_has) {  // the reference returns None; the fixed-shape buffer gets zeros
+        for (int i = tid; i < rp.size; i += nt) out[i] = 0.0f;
+        return;
+    }
+    const float lx = s_loc[0], ly = s_loc[1];
+    int off = 0;
+    ram_nearest_points(key, rp.sort_cap, rec + L.pellet_x, rec + L.pellet_y, p.c.num_pellets, true, lx, ly, rp.n_pellet, out + off);
+    off += 2 * rp.n_pellet;
+    ram_nearest_points(key, rp.sort_cap, rec + L.virus_x, rec + L.virus_y, p.c.num_viruses, false, lx, ly, rp.n_virus, out + off);
+    off += 2 * rp.n_virus;
+    ram_nearest_points(key, rp.sort_cap, rec + L.food_x, rec + L.food_y, p.c.max_foods, true, lx, ly, rp.n_food, out + off);
+    off += 2 * rp.n_food;
+    // the agent's own cells: absolute coordinates (relative=False, :131)
+    if (warp == 0)
+        ram_player_cells(cx + a * MC, cy + a * MC, cix + a * MC, ciy + a * MC, cm + a * MC, lx, ly, false, rp.n_cell, out + off, lane);
+    off += 5 * rp.n_cell;
+    // closest_players (:186-193): the other players that have cells, by distance between centroids
+    // (float32 sqrt(dx*dx + dy*dy)), ties by player index
+    for (int k = warp; k < 64; k += nt >> 5) {
+        unsigned long long kk = ~0ull;
+        if (k < K && k != a) {  // warp-uniform
+            const int g = k * MC + (lane & 15);
+            const bool v = lane < MC;
+            float qx = 0.0f, qy = 0.0f;
+            const bool has = hw_centroid(0, lane & 15, v ? cx[g] : 0.0f, v ? cy[g] : 0.0f, v ? cm[g] : 0.0f, qx, qy);
+            if (has) {
+                const float dx = lx - qx, dy = ly - qy;
+                kk = ((unsigned long long)__float_as_uint(sqrtf(dx * dx + dy * dy)) << 32) | (unsigned)k;
+            }
+        }
+        if (lane == 0) pkey[k] = kk;
+    }
+    __syncthreads();
+    bitonic_sort_u64(pkey, 64);
+    for (int j = warp; j < rp.n_other; j += nt >> 5) {  // one warp per selected player
+        float* o = out + off + 5 * rp.n_cell * j;
+        const unsigned long long kk = j < 64 ? pkey[j] : ~0ull;
+        if (kk == ~0ull) {  // not enough players: filler rows (:139-141)
+            for (int r = lane; r < 5 * rp.n_cell; r += 32) o[r] = rp.filler;
+        } else {
+            const int k = (int)(unsigned)kk;
+            ram_player_cells(cx + k * MC, cy + k * MC, cix + k * MC, ciy + k * MC, cm + k * MC, lx, ly, true, rp.n_cell, o, lane);
+        }
+    }
+}
+
+}  // namespace agar

@@ -245,6 +245,25 @@ int agar_gae(const float* d_reward, const float* d_value, const uint8_t* d_done,
              const float* d_end_value, double gamma, double lam, float* d_adv, float* d_ret,
              int32_t T, int32_t N, void* stream);
 
+/* FeatureExtractor.extract — features/extractors.py:99-149 (helpers :171-212), the fixed-length "RAM-style"
+ * observation the DQN trainer consumes (dqn/train.py:89-96): for every agent of every arena, from the current
+ * state,  [nearest n_pellet pellets | n_virus viruses | n_food foods] as (x, y) relative to the agent's
+ * centroid, the agent's own cells (absolute) and the n_other closest players' cells (relative), n_cell rows
+ * of (x, y, impulse_x, impulse_y, mass) each; zero rows pad missing entities, -1000 rows missing players.
+ * size = 2*(n_pellet+n_virus+n_food) + 5*(1+n_other)*n_cell (580 with the reference defaults 50,5,10,5,15).
+ * d_out float[N, A, size].  An agent without cells gets zeros (the reference returns None).
+ * Distance ties keep index order (numpy leaves them unspecified); `largest_cells` keeps the n_cell SMALLEST
+ * cells, as the reference does (argsort ascending, :182-184). */
+int agar_ram_feature_size(int32_t n_pellet, int32_t n_virus, int32_t n_food, int32_t n_other,
+                          int32_t n_cell);
+int agar_observe_ram(AgarEnv* env, int32_t n_pellet, int32_t n_virus, int32_t n_food, int32_t n_other,
+                     int32_t n_cell, float* d_out, void* stream);
+
+/* ScreenFeatureExtractor.extract — features/extractors.py:152-164: mean over the trailing colour axis of
+ * uint8 frames, d_rgb uint8[n_pixels, 3] -> d_out float64[n_pixels] (out_f64 != 0: the reference's dtype,
+ * bit-exact) or float32[n_pixels] (that value rounded once).  Needs no env handle. */
+int agar_screen_gray(const uint8_t* d_rgb, int64_t n_pixels, void* d_out, int32_t out_f64, void* stream);
+
 /* number of kernel launches issued by this handle since creation (bench bookkeeping) */
 int64_t agar_launch_count(const AgarEnv* env);
 

@@ -597,6 +597,139 @@ static void observe_arena(const OracleEnv* e, const float* S, float* obs /* [A,C
                             obs + (size_t)a * C * G * G);
 }
 
+
+/* ------------------------------------------------------- RAM-style feature extractor --- */
+/* FeatureExtractor.extract (features/extractors.py:99-149) and its helpers (:171-212) for one
+ * agent, on float32 inputs (numpy then evaluates every step below in float32):
+ *   loc = position(agent)                                   (:207-212, centroid16 above)
+ *   get_entity_features(loc, E, n)  (:171-180): rows of E ordered by
+ *       np.linalg.norm(E[:, :2] - loc, axis=1) = sqrtf(dx*dx + dy*dy), first n, (x, y) -= loc,
+ *       zero rows pad.  numpy's default argsort leaves the order of equal keys unspecified; this
+ *       restatement (and the CUDA kernel) keep index order (the stable sort).
+ *   largest_cells(player, n)        (:182-184): argsort ASCENDING by mass, first n rows - the
+ *       n smallest cells (reference quirk, reproduced); stable.
+ *   closest_players(loc, others, n) (:186-193): by sqrtf(dx*dx + dy*dy) between centroids; stable.
+ *       `others` = the other players that have at least one cell, in player order (own spec).
+ *   missing players are filled with -1000 rows (:139-141, filler_value :110).
+ * Cell rows are (x, y, impulse_x, impulse_y, mass): the reference never reads columns 2-3.
+ * out: float[2*(np+nv+nf) + 5*(1+no)*nc].  Returns 0 and zeros if the agent has no cell (the
+ * reference returns None). */
+typedef struct { float d; int i; } DistIdx;
+
+static void stable_sort_dist(DistIdx* a, int n) {  /* insertion sort: stable, n is small or moderate */
+    for (int i = 1; i < n; ++i) {
+        DistIdx v = a[i];
+        int j = i - 1;
+        while (j >= 0 && a[j].d > v.d) { a[j + 1] = a[j]; --j; }
+        a[j + 1] = v;
+    }
+}
+
+static void ram_points(const float* ex, const float* ey, int count, int marker, float lx, float ly, int n, float* out) {
+    DistIdx* a = (DistIdx*)malloc(sizeof(DistIdx) * (size_t)(count > 0 ? count : 1));
+    int m = 0;
+    for (int i = 0; i < count; ++i) {
+        if (marker && !(ex[i] >= 0.0f)) continue;
+        float dx = ex[i] - lx, dy = ey[i] - ly;
+        float s0 = dx * dx, s1 = dy * dy;
+        a[m].d = sqrtf(s0 + s1); a[m].i = i; ++m;
+    }
+    stable_sort_dist(a, m);
+    for (int r = 0; r < n; ++r) {
+        if (r < m) { out[2 * r] = ex[a[r].i] - lx; out[2 * r + 1] = ey[a[r].i] - ly; }
+        else { out[2 * r] = 0.0f; out[2 * r + 1] = 0.0f; }
+    }
+    free(a);
+}
+
+static void ram_cells(const float* cx, const float* cy, const float* cix, const float* ciy, const float* cm,
+                      float lx, float ly, int relative, int n, float* out) {
+    DistIdx bym[MC]; int na = 0;
+    for (int s = 0; s < MC; ++s)
+        if (cm[s] > 0.0f) { bym[na].d = cm[s]; bym[na].i = s; ++na; }
+    stable_sort_dist(bym, na);                    /* largest_cells: ascending by mass */
+    int nsel = na < n ? na : n;
+    DistIdx byd[MC];
+    for (int r = 0; r < nsel; ++r) {
+        int s = bym[r].i;
+        float dx = cx[s] - lx, dy = cy[s] - ly;
+        float s0 = dx * dx, s1 = dy * dy;
+        byd[r].d = sqrtf(s0 + s1); byd[r].i = s;
+    }
+    stable_sort_dist(byd, nsel);                  /* sort_by_proximity on the selected rows */
+    for (int r = 0; r < n; ++r) {
+        float* o = out + 5 * r;
+        if (r < nsel) {
+            int s = byd[r].i;
+            o[0] = relative ? cx[s] - lx : cx[s]; o[1] = relative ? cy[s] - ly : cy[s];
+            o[2] = cix[s]; o[3] = ciy[s]; o[4] = cm[s];
+        } else { o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f; }
+    }
+}
+
+int oracle_ram_feature_size(int np_, int nv, int nf, int no, int nc) { return 2 * (np_ + nv + nf) + 5 * (1 + no) * nc; }
+
+int oracle_ram_extract(int n_pellet, int n_virus, int n_food, int n_other, int n_cell, int agent, int K,
+                       const float* pel_x, const float* pel_y, int P,
+                       const float* vir_x, const float* vir_y, int V,
+                       const float* food_x, const float* food_y, int F,
+                       const float* cell_x, const float* cell_y, const float* cell_ix, const float* cell_iy,
+                       const float* cell_m, /* [K*16] */
+                       float* out) {
+    int size = oracle_ram_feature_size(n_pellet, n_virus, n_food, n_other, n_cell);
+    memset(out, 0, sizeof(float) * (size_t)size);
+    float lx, ly;
+    if (!centroid16(cell_x + agent * MC, cell_y + agent * MC, cell_m + agent * MC, &lx, &ly)) return 0;
+    float* o = out;
+    ram_points(pel_x, pel_y, P, 1, lx, ly, n_pellet, o); o += 2 * n_pellet;
+    ram_points(vir_x, vir_y, V, 0, lx, ly, n_virus, o); o += 2 * n_virus;
+    ram_points(food_x, food_y, F, 1, lx, ly, n_food, o); o += 2 * n_food;
+    int g = agent * MC;
+    ram_cells(cell_x + g, cell_y + g, cell_ix + g, cell_iy + g, cell_m + g, lx, ly, 0, n_cell, o); o += 5 * n_cell;
+    DistIdx pl[64]; int npl = 0;
+    for (int k = 0; k < K; ++k) {
+        if (k == agent) continue;
+        float qx, qy;
+        if (!centroid16(cell_x + k * MC, cell_y + k * MC, cell_m + k * MC, &qx, &qy)) continue;
+        float dx = lx - qx, dy = ly - qy;
+        float s0 = dx * dx, s1 = dy * dy;
+        pl[npl].d = sqrtf(s0 + s1); pl[npl].i = k; ++npl;
+    }
+    stable_sort_dist(pl, npl);
+    for (int j = 0; j < n_other; ++j) {
+        if (j < npl) {
+            int g2 = pl[j].i * MC;
+            ram_cells(cell_x + g2, cell_y + g2, cell_ix + g2, cell_iy + g2, cell_m + g2, lx, ly, 1, n_cell, o);
+        } else {
+            for (int r = 0; r < 5 * n_cell; ++r) o[r] = -1000.0f;
+        }
+        o += 5 * n_cell;
+    }
+    return 1;
+}
+
+/* FeatureExtractor for every agent of every arena of the env's current state: float[N, A, size] */
+void oracle_observe_ram(const OracleEnv* e, int n_pellet, int n_virus, int n_food, int n_other, int n_cell, float* out) {
+    const AgarConfig* c = &e->cfg; const AgarLayout* L = &e->L;
+    int size = oracle_ram_feature_size(n_pellet, n_virus, n_food, n_other, n_cell);
+    for (int n = 0; n < c->num_arenas; ++n) {
+        const float* S = e->state + (size_t)n * L->words;
+        for (int a = 0; a < c->num_agents; ++a)
+            oracle_ram_extract(n_pellet, n_virus, n_food, n_other, n_cell, a, L->num_players,
+                               S + L->pellet_x, S + L->pellet_y, c->num_pellets, S + L->virus_x, S + L->virus_y, c->num_viruses,
+                               S + L->food_x, S + L->food_y, c->max_foods, S + L->cell_x, S + L->cell_y, S + L->cell_ix,
+                               S + L->cell_iy, S + L->cell_m, out + ((size_t)n * c->num_agents + a) * size);
+    }
+}
+
+/* ------------------------------------------------------------- screen -> grayscale --- */
+/* ScreenFeatureExtractor.extract (features/extractors.py:152-164): observation.mean(axis=-1) of
+ * uint8 frames: numpy adds the three bytes in float64 and divides by the count. */
+void oracle_screen_gray(const uint8_t* rgb, long long n_pixels, double* out) {
+    for (long long p = 0; p < n_pixels; ++p)
+        out[p] = ((double)rgb[3 * p] + (double)rgb[3 * p + 1] + (double)rgb[3 * p + 2]) / 3.0;
+}
+
 /* ---------------------------------------------------------------------- public API --- */
 OracleEnv* oracle_create(const AgarConfig* cfg) {
     if (agar_spec_config_check(cfg)) return NULL;

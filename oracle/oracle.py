@@ -87,6 +87,13 @@ def lib():
         L.oracle_grid_extract.argtypes = [C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
                                           f32p, f32p, C.c_int, f32p, f32p, C.c_int, f32p, f32p, C.c_int,
                                           f32p, f32p, f32p, f32p]
+        L.oracle_ram_feature_size.restype = C.c_int
+        L.oracle_ram_feature_size.argtypes = [C.c_int] * 5
+        L.oracle_ram_extract.restype = C.c_int
+        L.oracle_ram_extract.argtypes = [C.c_int] * 7 + [f32p, f32p, C.c_int, f32p, f32p, C.c_int, f32p, f32p, C.c_int,
+                                                       f32p, f32p, f32p, f32p, f32p, f32p]
+        L.oracle_observe_ram.argtypes = [C.c_void_p] + [C.c_int] * 5 + [f32p]
+        L.oracle_screen_gray.argtypes = [u8p, C.c_longlong, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -179,6 +186,12 @@ class OracleEnv:
         assert s.shape == (self.N, self.L.words)
         lib().oracle_set_state(self._h, _p(s, C.c_float))
 
+    def observe_ram(self, n_pellet=50, n_virus=5, n_food=10, n_other=5, n_cell=15):
+        size = lib().oracle_ram_feature_size(n_pellet, n_virus, n_food, n_other, n_cell)
+        out = np.empty((self.N, self.A, size), np.float32)
+        lib().oracle_observe_ram(self._h, n_pellet, n_virus, n_food, n_other, n_cell, _p(out, C.c_float))
+        return out
+
     def events(self):
         cap = self.cfg.event_capacity
         ev = np.zeros((self.N, max(cap, 1), 4), np.int32)
@@ -235,3 +248,27 @@ def grid_extract(G, view, arena, flags, agent, K, pellets, viruses, foods, cell_
                                    _p(vx, C.c_float), _p(vy, C.c_float), V, _p(fx, C.c_float), _p(fy, C.c_float), F,
                                    _p(cx, C.c_float), _p(cy, C.c_float), _p(cm, C.c_float), _p(out, C.c_float))
     return out, bool(ok)
+
+
+def ram_extract(counts, agent, K, pellets, viruses, foods, cell_x, cell_y, cell_ix, cell_iy, cell_m):
+    """oracle_ram_extract on raw entity arrays (FeatureExtractor.extract, features/extractors.py:99-149);
+    counts = (n_pellet, n_virus, n_food, n_other, n_cell); pellets/viruses/foods are [n,2] float32."""
+    def split(a):
+        a = np.ascontiguousarray(a, np.float32).reshape(-1, 2)
+        return np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1]), a.shape[0]
+    px, py, P = split(pellets); vx, vy, V = split(viruses); fx, fy, F = split(foods)
+    arrs = [np.ascontiguousarray(a, np.float32) for a in (cell_x, cell_y, cell_ix, cell_iy, cell_m)]
+    assert all(a.shape == (K * 16,) for a in arrs)
+    out = np.empty(lib().oracle_ram_feature_size(*counts), np.float32)
+    ok = lib().oracle_ram_extract(*counts, agent, K, _p(px, C.c_float), _p(py, C.c_float), P, _p(vx, C.c_float),
+                                  _p(vy, C.c_float), V, _p(fx, C.c_float), _p(fy, C.c_float), F,
+                                  *[_p(a, C.c_float) for a in arrs], _p(out, C.c_float))
+    return out, bool(ok)
+
+
+def screen_gray(rgb):
+    """oracle_screen_gray: uint8[..., 3] -> float64[...] (ScreenFeatureExtractor.extract, :152-164)."""
+    a = np.ascontiguousarray(rgb, np.uint8)
+    out = np.empty(a.shape[:-1], np.float64)
+    lib().oracle_screen_gray(_p(a, C.c_uint8), out.size, _p(out, C.c_double))
+    return out

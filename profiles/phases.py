@@ -26,30 +26,33 @@ for r in rows:
             pass
 src = open("agarai_b200/csrc/agar_kernels.cuh").read().split("\n")
 MARKS = [
-    ("device helpers (philox, half-warp sums)", "namespace agar {"),
-    ("build_hash", "__device__ void build_hash"),
+    ("device helpers (philox, sums, TMA)", "namespace agar {"),
+    ("reset_arena (out of line)", "__device__ __noinline__ void reset_arena"),
+    ("build_hash (out of line)", "__device__ __noinline__ void build_hash"),
     ("build_list", "__device__ __forceinline__ void build_list"),
-    ("raster: setup, centroids, oob flags", "__device__ void raster_arena"),
-    ("raster: pellets via hash window", "// pellets under the view window"),
-    ("raster: point entities full scan", "// point entities: value 1 each"),
-    ("raster: mass channels (ordered)", "// cell rows: value = mass"),
-    ("raster: write-out", "// write the channel out with 128-bit"),
-    ("kernel: prelude + stage record", "template <int kThreads>"),
-    ("step start: hash+list, players", "// ---- pellet hash, alive list ----"),
+    ("raster helpers (bins, ordered sums)", "__device__ __noinline__ float div_rn"),
+    ("raster: centroids, setup", "__device__ void raster_arena"),
+    ("raster: gather others", "// ---- gather: other players' cells in view"),
+    ("raster: base image stores", "// ---- base image of every channel"),
+    ("raster: mass patches (warp 0)", "// ---- warp 0: own cells and others"),
+    ("raster: count channels", "// ---- count channels ----"),
+    ("virus pops (out of line)", "__device__ __noinline__ void virus_pops"),
+    ("kernel: prelude + stage record", "template <int kThreads, int kMinBlocks>"),
+    ("step start: hash check, list", "// ---- pellet hash (persisted across steps"),
+    ("step start: players", "// ---- players: bot respawn, centroid"),
     ("step start: multi-cell players", "// ---- players with several cells"),
     ("step start: agent actions", "// ---- agents: action -> target point"),
     ("step start: bots", "// ---- bots: nearest pellet in the square"),
     ("step start: split", "// ---- split: i-th eligible"),
     ("step start: feed", "// ---- feed: cells in gid order"),
     ("tick: motion + pellet query", "for (int tk = 0; tk < c.ticks_per_step"),
-    ("tick: resolve pellets", "// ---- resolve the claimed pellets"),
-    ("tick: foods", "const bool food_any"),
-    ("tick: apply gains + virus claim", "// ---- apply gains (pellets, or foods"),
-    ("tick: virus pops", "// ---- virus pops ----"),
-    ("tick: cell eats cell", "// ---- cell eats cell (different players) on the pre-phase"),
+    ("tick: resolve pellets, foods", "// ---- resolve the claimed pellets"),
+    ("tick: eat test lambda + apply gains", "// cell-eats-cell test (different players"),
+    ("tick: eat loop, eat apply", "// ---- cell eats cell (one code site)"),
     ("tick: merge", "// ---- merge own cells whose timers ran out"),
-    ("rewards / dones", "// ---- rewards / dones ----"),
-    ("write back", "// ---- write back ----"),
+    ("rewards / dones, auto reset", "// ---- rewards / dones ----"),
+    ("persist hash", "// ---- persist the pellet hash"),
+    ("write back", "// ---- write back:"),
     ("observations call", "// ---- observations ----"),
     ("gae kernel", "// rl.gae / rl.make_returns (rl/__init__.py:94-159"),
 ]

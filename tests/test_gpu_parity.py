@@ -393,3 +393,63 @@ def test_raster_crowded_view_more_than_32_other_cells(oracle):
     assert np.array_equal(got.view(np.int32), exp.view(np.int32))
     assert (exp[:, :, 2] > 0).sum(axis=(2, 3)).max() > 20  # the others channel really is crowded
     env.close()
+
+
+def test_ram_features_match_oracle_and_reference_golden(oracle):
+    """FeatureExtractor (features/extractors.py:99-149) on the device: (1) the reference's own outputs on the
+    golden entity sets, loaded as engine state; (2) the oracle on states reached by stepping dense worlds,
+    including agents without cells, fresh splits (equal keys) and fewer players than slots."""
+    import agarai_b200 as ab
+    z = np.load(os.path.join(GOLD, "ram_golden.npz"))
+    for i in range(int(z["n"])):
+        g = {k: z[f"{k}_{i}"] for k in ("counts", "K", "px", "py", "vx", "vy", "fx", "fy", "cx", "cy", "cix", "ciy", "cm", "expect")}
+        K = int(g["K"])
+        cfg = ab.default_config(num_arenas=1, num_agents=1, num_bots=K - 1, num_pellets=len(g["px"]),
+                                num_viruses=len(g["vx"]), max_foods=len(g["fx"]))
+        env = ab.BatchedAgarioEnv(cfg, device="cuda:0", seed=0)
+        L = env.layout
+        st = np.zeros((1, L.words), np.float32)
+        st[0, L.pellet_x:L.pellet_x + L.P_pad] = -1.0
+        st[0, L.food_x:L.food_x + L.F_pad] = -1.0
+        for name, off in (("px", L.pellet_x), ("py", L.pellet_y), ("vx", L.virus_x), ("vy", L.virus_y), ("fx", L.food_x),
+                          ("fy", L.food_y), ("cx", L.cell_x), ("cy", L.cell_y), ("cix", L.cell_ix), ("ciy", L.cell_iy),
+                          ("cm", L.cell_m)):
+            st[0, off:off + len(g[name])] = g[name]
+        env.set_state(torch.from_numpy(st))
+        ex = ab.FeatureExtractor(*[int(v) for v in g["counts"]])
+        got = ex.extract(env).cpu().numpy()[0, 0]
+        assert np.array_equal(got.astype(np.float64), g["expect"]), f"golden case {i}"
+        env.close()
+    # oracle on evolving states
+    genv, oenv = make_pair(oracle, seed=21, num_arenas=6, num_agents=3, num_bots=4, num_viruses=5, num_pellets=300,
+                           max_foods=16, arena_size=100.0, start_mass=40.0, merge_delay=12.0, auto_reset=0,
+                           virus_mass=30.0, virus_pop_mass=60.0, speed_k=6.0)
+    genv.reset(); oenv.reset()
+    rng = np.random.default_rng(3)
+    for counts in ((50, 5, 10, 5, 15), (7, 3, 2, 9, 16), (400, 8, 32, 2, 1)):
+        ex = ab.FeatureExtractor(*counts)
+        for t in range(25):
+            xy, act = random_actions(rng, 6, 3, (0, 1, 2), 0.6)
+            genv.step(torch.from_numpy(xy).cuda(), torch.from_numpy(act).cuda(), want_obs=False)
+            oenv.step(xy, act, want_obs=False)
+            got = ex.extract(genv).cpu().numpy()
+            want = oenv.observe_ram(*counts)
+            assert np.array_equal(got.view(np.int32), want.view(np.int32)), f"{counts} step {t}"
+    genv.close()
+
+
+def test_screen_gray_matches_reference_golden(oracle):
+    """ScreenFeatureExtractor.extract (features/extractors.py:152-164): float64 bit-exact against the
+    reference's outputs; float32 = that value rounded once; ragged tail; full-size property check."""
+    import agarai_b200 as ab
+    z = np.load(os.path.join(GOLD, "screen_golden.npz"))
+    ex = ab.ScreenFeatureExtractor(2, 40)
+    for key, want in (("frames", "gray"), ("odd", "odd_gray")):
+        x = torch.from_numpy(z[key]).cuda()
+        assert np.array_equal(ex.extract(x).cpu().numpy(), z[want])
+        assert np.array_equal(ex.extract(x, dtype=torch.float32).cpu().numpy(), z[want].astype(np.float32))
+    big = torch.randint(0, 256, (64, 4, 128, 128, 3), dtype=torch.uint8, device="cuda")   # dqn: 4 frames of 128x128
+    got = ex.extract(big)
+    assert np.array_equal(got.cpu().numpy(), big.cpu().numpy().mean(axis=-1))  # numpy's own statement, full size
+    assert np.array_equal(got[:2].cpu().numpy(), oracle.screen_gray(big[:2].cpu().numpy()))
+    assert ex.extract(big[:0]).shape == (0, 4, 128, 128)

@@ -175,3 +175,44 @@ def test_env_multithreaded_step_is_identical(oracle):
         oa = a.step(xy, act); ob = b.step(xy, act)
         assert all(np.array_equal(x, y) for x, y in zip(oa, ob))
     assert np.array_equal(a.get_state().view(np.int32), b.get_state().view(np.int32))
+
+
+# ---------------------------------------------------------------- RAM-style / screen extractors
+def load_ram_cases():
+    z = np.load(os.path.join(GOLD, "ram_golden.npz"))
+    keys = ("counts", "K", "px", "py", "vx", "vy", "fx", "fy", "cx", "cy", "cix", "ciy", "cm", "expect")
+    return [{k: z[f"{k}_{i}"] for k in keys} for i in range(int(z["n"]))]
+
+
+def test_ram_extract_matches_reference(oracle):
+    """FeatureExtractor.extract (features/extractors.py:99-149) run from /root/reference on 32 entity sets:
+    the C restatement reproduces every element bit for bit (float32 values in the reference's float64 vector)."""
+    cases = load_ram_cases()
+    assert len(cases) == 32
+    for c in cases:
+        counts = tuple(int(v) for v in c["counts"])
+        got, ok = oracle.ram_extract(counts, 0, int(c["K"]), np.stack([c["px"], c["py"]], 1), np.stack([c["vx"], c["vy"]], 1),
+                                     np.stack([c["fx"], c["fy"]], 1), c["cx"], c["cy"], c["cix"], c["ciy"], c["cm"])
+        assert ok and got.shape == c["expect"].shape
+        assert np.array_equal(got.astype(np.float64), c["expect"]), counts
+
+
+def test_ram_extract_agent_without_cells_and_stable_ties(oracle):
+    K = 2
+    z = np.zeros(K * 16, np.float32)
+    out, ok = oracle.ram_extract((3, 1, 1, 1, 2), 0, K, np.zeros((4, 2), np.float32), np.zeros((0, 2), np.float32),
+                                 np.zeros((0, 2), np.float32), z, z, z, z, z)
+    assert not ok and not out.any()
+    # two pellets at the same distance: the lower index comes first (own spec: numpy leaves it open)
+    cm = z.copy(); cm[0] = 10.0
+    cx = z.copy(); cy = z.copy(); cx[0] = 50.0; cy[0] = 50.0
+    pel = np.array([[53, 54], [47, 46], [50, 51]], np.float32)
+    out, ok = oracle.ram_extract((3, 0, 0, 0, 1), 0, K, pel, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32),
+                                 cx, cy, z, z, cm)
+    assert ok and out[:6].tolist() == [0, 1, 3, 4, -3, -4]
+
+
+def test_screen_gray_matches_reference(oracle):
+    z = np.load(os.path.join(GOLD, "screen_golden.npz"))
+    assert np.array_equal(oracle.screen_gray(z["frames"]), z["gray"])
+    assert np.array_equal(oracle.screen_gray(z["odd"]), z["odd_gray"])
