@@ -11,10 +11,11 @@ from .env import BatchedAgarioEnv, GymCompatEnv, config_from_gym_kwargs, make
 from .features import FeatureExtractor, GridFeatureExtractor, ScreenFeatureExtractor
 from .gae import gae, gae_and_returns, make_returns
 from .rollout import DeviceRollout
+from .vector import Coordinator, RemoteEnvironment
 
 __all__ = [
     "AgarConfig", "AgarError", "AgarLayout", "default_config", "ActionConfig", "ActionConverter",
     "action_size", "ppo_action_table", "unravel_action_table", "BatchedAgarioEnv", "GymCompatEnv",
     "config_from_gym_kwargs", "make", "gae", "gae_and_returns", "make_returns", "DeviceRollout",
-    "FeatureExtractor", "GridFeatureExtractor", "ScreenFeatureExtractor",
+    "FeatureExtractor", "GridFeatureExtractor", "ScreenFeatureExtractor", "Coordinator", "RemoteEnvironment",
 ]

@@ -24,8 +24,10 @@ from .actions import ActionConfig, ppo_action_table
 OBS_PELLETS, OBS_CELLS, OBS_OTHERS, OBS_VIRUSES, OBS_FOODS = 1, 2, 4, 8, 16
 
 # gym ids the reference uses (configuration/__init__.py:38-42, dqn/hyperparameters.py:89)
-GYM_IDS = ("agario-grid-v0",)
-_UNSUPPORTED_IDS = ("agario-ram-v0", "agario-screen-v0", "agario-full-v0")
+GYM_IDS = ("agario-grid-v0", "agario-ram-v0")
+# screen frames are drawn by the external package's renderer (only their grayscale reduction is in the
+# reference tree: features.ScreenFeatureExtractor); "full" hands out raw entity lists, see full_observation()
+_UNSUPPORTED_IDS = ("agario-screen-v0", "agario-full-v0")
 
 # `difficulty` only selects defaults in the original package; explicit kwargs win
 _DIFFICULTY_DEFAULTS = {
@@ -112,8 +114,12 @@ class BatchedAgarioEnv:
 
     metadata = {"render.modes": []}
 
-    def __init__(self, cfg: "_lib.AgarConfig", device=None, seed: int = 0, action_config: ActionConfig = None):
+    def __init__(self, cfg: "_lib.AgarConfig", device=None, seed: int = 0, action_config: ActionConfig = None,
+                 observation: str = "grid", ram_extractor=None):
         self._h = None
+        if observation not in ("grid", "ram"):
+            raise ValueError("observation must be 'grid' or 'ram'")
+        self.observation = observation
         self._L = _lib.lib()
         if not torch.cuda.is_available():
             raise _lib.AgarError("BatchedAgarioEnv needs a CUDA device (there is no CPU fallback)")
@@ -132,6 +138,12 @@ class BatchedAgarioEnv:
         # per-agent spaces, as the reference's consumers read them (dqn/qn.py:50 takes shape[0] as
         # channels => CHW, which is also GridFeatureExtractor.shape, features/extractors.py:31)
         self.observation_space = Box(-1.0, np.inf, (self.channels, G, G))
+        self.ram_extractor = None
+        if observation == "ram":  # agario-ram-v0: FeatureExtractor vectors (features/extractors.py:99-149)
+            from .features import FeatureExtractor
+            self.ram_extractor = ram_extractor or FeatureExtractor()
+            self.obs_shape = (self.num_envs, self.num_agents, self.ram_extractor.size)
+            self.observation_space = Box(-np.inf, np.inf, self.ram_extractor.shape)
         self.action_space = TupleSpace((Box(-1.0, 1.0, (2,)), Discrete(3)))
         self.action_config = action_config or ActionConfig()
         self.set_action_table(*ppo_action_table(self.action_config))
@@ -164,8 +176,9 @@ class BatchedAgarioEnv:
         obs = self._new_obs() if out_obs is None else out_obs
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
-        _lib.check(self._L.agar_reset(self._h, _ptr(mask), _ptr(obs), self._stream()))
-        return obs
+        ram = self.ram_extractor is not None
+        _lib.check(self._L.agar_reset(self._h, _ptr(mask), None if ram else _ptr(obs), self._stream()))
+        return self.ram_extractor.extract(self, out=obs) if ram else obs
 
     def _outs(self, out_obs, want_obs):
         obs = (self._new_obs() if out_obs is None else out_obs) if want_obs else None
@@ -179,7 +192,11 @@ class BatchedAgarioEnv:
         if t.numel() != self.num_envs * self.num_agents * 2 or a.numel() != self.num_envs * self.num_agents:
             raise ValueError("step: actions must be [num_envs, num_agents, 2] and [num_envs, num_agents]")
         obs, reward, done = self._outs(out_obs, want_obs)
-        _lib.check(self._L.agar_step(self._h, _ptr(t), _ptr(a), _ptr(obs), _ptr(reward), _ptr(done), self._stream()))
+        ram = self.ram_extractor is not None
+        _lib.check(self._L.agar_step(self._h, _ptr(t), _ptr(a), None if ram else _ptr(obs), _ptr(reward), _ptr(done),
+                                     self._stream()))
+        if ram and obs is not None:
+            self.ram_extractor.extract(self, out=obs)
         return obs, reward, done, {}
 
     def set_action_table(self, xy: np.ndarray, act: np.ndarray):
@@ -195,11 +212,17 @@ class BatchedAgarioEnv:
         if idx.numel() != self.num_envs * self.num_agents:
             raise ValueError("step_discrete: indices must be [num_envs, num_agents]")
         obs, reward, done = self._outs(out_obs, want_obs)
-        _lib.check(self._L.agar_step_indexed(self._h, _ptr(idx), _ptr(obs), _ptr(reward), _ptr(done), self._stream()))
+        ram = self.ram_extractor is not None
+        _lib.check(self._L.agar_step_indexed(self._h, _ptr(idx), None if ram else _ptr(obs), _ptr(reward), _ptr(done),
+                                             self._stream()))
+        if ram and obs is not None:
+            self.ram_extractor.extract(self, out=obs)
         return obs, reward, done, {}
 
     def observe(self, out_obs=None):
         obs = self._new_obs() if out_obs is None else out_obs
+        if self.ram_extractor is not None:
+            return self.ram_extractor.extract(self, out=obs)
         _lib.check(self._L.agar_observe(self._h, _ptr(obs), self._stream()))
         return obs
 
@@ -244,6 +267,10 @@ class BatchedAgarioEnv:
         if obs is not None and (obs.dtype != np.float32 or not obs.flags.c_contiguous or obs.size != int(np.prod(self.obs_shape))):
             raise ValueError("step_host: bad obs buffer")
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        if self.ram_extractor is not None and obs is not None:  # feature vectors: a second launch, then one copy
+            _lib.check(self._L.agar_step_host(self._h, vp(target_xy), vp(act), None, vp(reward), vp(done)))
+            torch.from_numpy(obs).copy_(self.ram_extractor.extract(self).reshape(obs.shape))
+            return
         _lib.check(self._L.agar_step_host(self._h, vp(target_xy), vp(act), vp(obs), vp(reward), vp(done)))
 
     @property
@@ -320,12 +347,14 @@ def make(env_id: str = "agario-grid-v0", num_envs: int = 1, device=None, seed: i
     """gym.make(env_id, **kwargs) for the batched engine.  With num_envs == 1 (and gym_compat not
     False) the reference-shaped per-arena view is returned; otherwise the batched tensor env."""
     if env_id in _UNSUPPORTED_IDS:
-        raise NotImplementedError(f"{env_id}: only the grid observation family is on the accelerated path")
+        raise NotImplementedError(f"{env_id}: the grid and ram observation families are on the accelerated path")
     if env_id not in GYM_IDS:
         raise ValueError(f"unknown env id {env_id!r}")
     multi_agent = bool(kwargs.get("multi_agent", True))
+    ram_extractor = kwargs.pop("ram_extractor", None)
     cfg = config_from_gym_kwargs(num_envs=num_envs, **kwargs)
-    env = BatchedAgarioEnv(cfg, device=device, seed=seed, action_config=action_config)
+    env = BatchedAgarioEnv(cfg, device=device, seed=seed, action_config=action_config,
+                           observation="ram" if env_id == "agario-ram-v0" else "grid", ram_extractor=ram_extractor)
     if gym_compat is None:
         gym_compat = num_envs == 1
     return GymCompatEnv(env, multi_agent=multi_agent) if gym_compat else env

@@ -94,3 +94,33 @@ class ScreenFeatureExtractor:
         _lib.check(_lib.lib().agar_screen_gray(_ptr(x), int(np.prod(x.shape[:-1])), _ptr(out),
                                                1 if dtype == torch.float64 else 0, _stream(x.device)))
         return out
+
+
+import collections
+
+FullObservation = collections.namedtuple("FullObservation", ["pellets", "viruses", "foods", "agent", "others"])
+
+
+def full_observation(env, arena: int = 0, agent: int = 0) -> "FullObservation":
+    """The raw entity lists of one agent's view, in the shape of the external package's `FullObservation`
+    that the reference's extractors read (features/extractors.py:40-64,108,140): present pellets / foods
+    [n,2], viruses [V,2], the agent's cells and every other player that has cells as [c,5] rows of
+    (x, y, impulse_x, impulse_y, mass).  Host-side view of the device state (a debugging and interop aid for
+    `agario-full-v0` style consumers; the accelerated extractors above never go through it)."""
+    L, c = env.layout, env.cfg
+    rec = env.get_state()[arena].cpu().numpy()
+    seg = lambda off, n: rec[off:off + n]
+    px, py = seg(L.pellet_x, c.num_pellets), seg(L.pellet_y, c.num_pellets)
+    fx, fy = seg(L.food_x, c.max_foods), seg(L.food_y, c.max_foods)
+    pellets = np.stack([px, py], 1)[px >= 0]
+    foods = np.stack([fx, fy], 1)[fx >= 0]
+    viruses = np.stack([seg(L.virus_x, c.num_viruses), seg(L.virus_y, c.num_viruses)], 1)
+
+    def player(k):
+        s = slice(k * 16, k * 16 + 16)
+        rows = np.stack([seg(L.cell_x, L.cells_total)[s], seg(L.cell_y, L.cells_total)[s], seg(L.cell_ix, L.cells_total)[s],
+                         seg(L.cell_iy, L.cells_total)[s], seg(L.cell_m, L.cells_total)[s]], 1)
+        return rows[rows[:, 4] > 0]
+
+    others = [p for p in (player(k) for k in range(L.num_players) if k != agent) if p.shape[0] > 0]
+    return FullObservation(pellets, viruses, foods, player(agent), others)

@@ -453,3 +453,74 @@ def test_screen_gray_matches_reference_golden(oracle):
     assert np.array_equal(got.cpu().numpy(), big.cpu().numpy().mean(axis=-1))  # numpy's own statement, full size
     assert np.array_equal(got[:2].cpu().numpy(), oracle.screen_gray(big[:2].cpu().numpy()))
     assert ex.extract(big[:0]).shape == (0, 4, 128, 128)
+
+
+def test_coordinator_matches_stand_alone_envs_and_reference_semantics(oracle):
+    """a2c/coordinator.py:17-100 on the batched engine: env i of the Coordinator is bit-identical to a
+    stand-alone gym-style env built with arena_id_base=i; finished envs return None and stay finished until
+    reset() (coordinator.py:43-66)."""
+    import agarai_b200 as ab
+    kw = dict(num_agents=1, multi_agent=False, difficulty="normal", num_pellets=200, num_viruses=3, num_bots=10, arena_size=50.0,
+              grid_size=32, observe_viruses=True, start_mass=12.0)
+    W = 5
+    singles = [ab.make("agario-grid-v0", seed=9, arena_id_base=i, **kw) for i in range(W)]
+    rng = np.random.default_rng(17)
+    with ab.Coordinator(lambda: kw, W, seed=9) as coord:
+        assert coord.observation_space().shape == singles[0].observation_space.shape
+        obs = coord.reset()
+        for i, e in enumerate(singles):
+            assert np.array_equal(obs[i], e.reset())
+        alive = [True] * W
+        for t in range(300):
+            acts = [(float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)), int(rng.integers(0, 3))) for _ in range(W)]
+            obs, rs, dones, infos = coord.step(acts)
+            for i, e in enumerate(singles):
+                if not alive[i]:
+                    assert obs[i] is None and rs[i] is None and infos[i] is None and dones[i]
+                    continue
+                o, r, d, _ = e.step(acts[i])
+                assert np.array_equal(obs[i], o) and rs[i] == r and dones[i] == d, (t, i)
+                alive[i] = not d
+        assert not all(alive), "no env finished in 300 steps: the sticky-done path was not exercised"
+        obs = coord.reset()
+        assert all(o is not None for o in obs) and coord.dones == [False] * W
+    for e in singles:
+        e.close()
+    # multi-agent env behind RemoteEnvironment (a2c/remote_environment.py:20-53)
+    mkw = dict(num_agents=3, difficulty="empty", num_pellets=100, arena_size=60.0, grid_size=16)
+    with ab.RemoteEnvironment(mkw, seed=2) as renv:
+        ref = ab.make("agario-grid-v0", seed=2, **mkw)
+        o1, o2 = renv.reset(), ref.reset()
+        assert all(np.array_equal(a, b) for a, b in zip(o1, o2))
+        acts = [(np.array([0.5, -0.5], np.float32), 0), (np.array([0.0, 1.0], np.float32), 1), (np.array([-1.0, 0.0], np.float32), 2)]
+        a1, a2 = renv.step(acts), ref.step(acts)
+        assert all(np.array_equal(a, b) for a, b in zip(a1[0], a2[0])) and np.array_equal(a1[1], a2[1]) and np.array_equal(a1[2], a2[2])
+        ref.close()
+
+
+def test_ram_env_id_and_full_observation_view(oracle):
+    """gym id agario-ram-v0 (configuration/__init__.py:38-42, dqn/train.py:89-96): observations are the
+    FeatureExtractor vectors; the FullObservation host view lists exactly what the extractor consumed."""
+    import agarai_b200 as ab
+    kw = dict(num_agents=2, difficulty="normal", num_pellets=120, num_viruses=4, num_bots=3, arena_size=90.0)
+    env = ab.make("agario-ram-v0", seed=4, **kw)          # the reference-shaped per-arena view
+    obs = env.reset()
+    assert len(obs) == 2 and obs[0].shape == (580,) == env.observation_space.shape
+    o, r, d, _ = env.step([(np.array([1.0, 0.0], np.float32), 0), (np.array([0.0, -1.0], np.float32), 1)])
+    want = ab.FeatureExtractor().extract(env.env).cpu().numpy()[0]
+    assert np.array_equal(o[0], want[0]) and np.array_equal(o[1], want[1])
+    full = ab.features.full_observation(env.env, arena=0, agent=1)
+    L = env.env.layout
+    st = env.env.get_state()[0].cpu().numpy()
+    got, ok = oracle.ram_extract((50, 5, 10, 5, 15), 1, L.num_players,
+                                 np.stack([st[L.pellet_x:L.pellet_x + 120], st[L.pellet_y:L.pellet_y + 120]], 1),
+                                 np.stack([st[L.virus_x:L.virus_x + 4], st[L.virus_y:L.virus_y + 4]], 1),
+                                 np.stack([st[L.food_x:L.food_x + 64], st[L.food_y:L.food_y + 64]], 1),
+                                 *[st[o_:o_ + L.cells_total] for o_ in (L.cell_x, L.cell_y, L.cell_ix, L.cell_iy, L.cell_m)])
+    assert ok and np.array_equal(got, o[1])
+    assert full.pellets.shape == (120, 2) and full.viruses.shape == (4, 2) and full.agent.shape[1] == 5
+    assert len(full.others) == 4 and all(p.shape[1] == 5 for p in full.others)
+    env.close()
+    benv = ab.make("agario-ram-v0", num_envs=16, seed=4, **kw)  # batched: torch tensors
+    assert tuple(benv.reset().shape) == (16, 2, 580)
+    benv.close()

@@ -202,3 +202,47 @@ def test_ppo_losses_match_reference_formulas():
     lo, v = net(torch.zeros(2, 3, 64, 64))
     assert lo.shape == (2, 9) and v.shape == (2,)
     assert net.dense.in_features == 52 * 52 * 5   # 13,520 features before the dense layer
+
+
+# ---- config front-end (configuration/__init__.py:26-73, environment.proto, config.proto) ----
+def test_textproto_config_front_end():
+    from agarai_b200 import configuration as cf
+    cfg = cf.load("ppo")
+    env = cfg.environment
+    assert cf.gym_env_name(env) == "agario-grid-v0"
+    kw = cf.gym_env_config(env)
+    assert list(kw) == ["num_agents", "multi_agent", "difficulty", "ticks_per_step", "arena_size", "num_pellets",
+                        "num_viruses", "num_bots", "pellet_regen", "grid_size", "num_frames", "observe_cells",
+                        "observe_others", "observe_pellets", "observe_viruses"]  # configuration/__init__.py:53-71
+    assert kw == dict(num_agents=16, multi_agent=True, difficulty="empty", ticks_per_step=4, arena_size=1000,
+                      num_pellets=1000, num_viruses=0, num_bots=0, pellet_regen=False, grid_size=64, num_frames=1,
+                      observe_cells=True, observe_others=True, observe_pellets=True, observe_viruses=False)
+    hp = cfg.hyperparameters
+    assert (hp.num_episodes, hp.episode_length, hp.num_sgd_steps, hp.batch_size) == (10000, 512, 8, 128)
+    assert hp.gamma == 0.75 and hp.gae.lam == 0.1 and hp.loss.ppo.clip_epsilon == 0.2
+    assert hp.critic_lr.scale == 10.0 and hp.actor_lr.scale == 1.0 and hp.actor_lr.exponential_decay.decay_steps == 500
+    assert hp.actor_lr.HasField("exponential_decay") and not hp.actor_lr.HasField("constant") and hp.seed == 0
+    assert cfg.model.feature_extractor.num_features == 1024 and not cfg.HasField("test_environment")
+    ac = cf.action_config(env)
+    assert ab.action_size(ac) == 9  # ppo.textproto:19-22: 1 + 8*1
+    # the kwargs feed straight into the engine's config mapping
+    ecfg = ab.config_from_gym_kwargs(num_envs=3, **kw)
+    assert (ecfg.num_agents, ecfg.num_pellets, ecfg.obs_flags, ecfg.pellet_regen) == (16, 1000, 7, 0)
+    # proto2 defaults and text-format details
+    m = cf.parse("environment { agario { difficulty: TRIVIAL } }  # configs/test_config.textproto:6-8")
+    assert m.environment.agario.difficulty == "TRIVIAL" and m.environment.num_agents == 1
+    assert m.environment.observation.grid_size == 64 and m.environment.observation.ticks_per_step == 4
+    assert cf.gym_env_config(m.environment)["difficulty"] == "trivial"
+    m = cf.parse('environment: < observation < type: 2 pellets: false > >; hyperparameters { gamma: 5e-1, seed: 0x10 }')
+    assert cf.gym_env_name(m.environment) == "agario-ram-v0" and m.hyperparameters.gamma == 0.5 and m.hyperparameters.seed == 16
+    with pytest.raises(ValueError):
+        cf.parse("hyperparameters { learning_rate: 0.1 }")  # configs/sweeps/gamma_lam.textproto:35 is rejected likewise
+    with pytest.raises(ValueError):
+        cf.parse("environment { agario { difficulty: EASY } }")  # configuration/test.py:13 names a value that does not exist
+    with pytest.raises(ValueError):
+        cf.parse("environment { num_agents: 2 ")
+    ref = "/root/reference/configuration/configs"
+    if os.path.isdir(ref):  # build container only: the reference's own files parse to the same kwargs
+        rcfg = cf.load(os.path.join(ref, "ppo.textproto"))
+        assert cf.gym_env_config(rcfg.environment) == kw and rcfg.hyperparameters.to_dict() == hp.to_dict()
+        assert cf.load(os.path.join(ref, "test_config.textproto")).environment.agario.difficulty == "TRIVIAL"
