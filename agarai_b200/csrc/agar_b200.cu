@@ -335,9 +335,14 @@ int agar_gae(const float* d_reward, const float* d_value, const uint8_t* d_done,
     if (d_adv && !d_value) return fail("agar_gae: advantages need d_value");
     if (!d_adv && !d_ret) return fail("agar_gae: nothing to compute");
     const float g = (float)gamma, cgl = (float)(gamma * lam);
-    const int threads = 128, blocks = (N + threads - 1) / threads;
-    agar_gae_kernel<8><<<blocks, threads, 0, (cudaStream_t)stream>>>(d_reward, d_value, d_done, d_end_value, g, cgl,
-                                                                  d_adv, d_ret, T, N);
+    // tuning switches (defaults are the measured best on B200, profiles/): steps per register batch and block size.
+    // A 4-columns-per-thread variant with 128-bit loads was measured slower (too few threads: 60 us vs 38 us).
+    static const int tune_u = std::getenv("AGAR_GAE_U") ? std::atoi(std::getenv("AGAR_GAE_U")) : 16;
+    static const int tune_b = std::getenv("AGAR_GAE_BLOCK") ? std::atoi(std::getenv("AGAR_GAE_BLOCK")) : 64;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = (tune_b == 32 || tune_b == 128 || tune_b == 256) ? tune_b : 64, blocks = (N + threads - 1) / threads;
+    if (tune_u == 8) agar_gae_kernel<8><<<blocks, threads, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N);
+    else agar_gae_kernel<16><<<blocks, threads, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N);
     CUDA_OK(cudaGetLastError());
     return 0;
 }

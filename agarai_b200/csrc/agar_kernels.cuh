@@ -1373,51 +1373,73 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
 
 // -------------------------------------------------------------------------------- GAE
 // rl.gae / rl.make_returns (rl/__init__.py:94-159; numpy statement rl/test.py:12-30) over a
-// time-major [T,N] rollout buffer: one thread per column, reverse scan over t with the loads of
-// U steps issued before the dependent chain so that enough bytes are in flight.
+// time-major [T,N] rollout buffer: one thread per column, reverse scan over t.  The recurrence is
+// sequential in t (and must stay so: the float sequence is the reference's), so the kernel is a
+// memory-latency problem: the loads of the NEXT batch of U steps are issued before the dependent
+// chain of the current batch runs (two register buffers), which keeps 2U rows in flight per thread.
 template <int U>
-__global__ void __launch_bounds__(128) agar_gae_kernel(const float* __restrict__ r, const float* __restrict__ v,
+struct GaeBatch { float r[U], v[U]; uint8_t d[U]; };
+
+template <int U>
+__device__ __forceinline__ void gae_load(GaeBatch<U>& b, const float* __restrict__ r, const float* __restrict__ v,
+                                         const uint8_t* __restrict__ done, bool want_v, int t1, int N, int n) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int t = t1 - 1 - u;
+        const bool ok = t >= 0;
+        const size_t i = (size_t)(ok ? t : 0) * N + n;
+        b.r[u] = ok ? __ldcs(r + i) : 0.0f;
+        b.v[u] = (ok && want_v) ? __ldcs(v + i) : 0.0f;
+        b.d[u] = (ok && done) ? __ldcs(done + i) : (uint8_t)0;
+    }
+}
+
+template <int U>
+__device__ __forceinline__ void gae_scan(const GaeBatch<U>& b, float g, float cgl, float* __restrict__ adv,
+                                         float* __restrict__ ret, int t1, int T, int N, int n, float& a_next,
+                                         float& g_next, float& v_next) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int t = t1 - 1 - u;
+        if (t < 0) break;
+        const size_t i = (size_t)t * N + n;
+        const bool cut = b.d[u] != 0;
+        if (adv) {
+            float vn = cut ? 0.0f : v_next;
+            float delta = (b.r[u] + g * vn) - b.v[u];
+            float av = (t == T - 1 || cut) ? delta : delta + cgl * a_next;
+            __stcs(adv + i, av);
+            a_next = av;
+            v_next = b.v[u];
+        }
+        if (ret) {
+            float gn = cut ? 0.0f : g_next;
+            float G_t = b.r[u] + g * gn;
+            __stcs(ret + i, G_t);
+            g_next = G_t;
+        }
+    }
+}
+
+template <int U>
+__global__ void __launch_bounds__(256) agar_gae_kernel(const float* __restrict__ r, const float* __restrict__ v,
                                                       const uint8_t* __restrict__ done,
                                                       const float* __restrict__ end_value, float g, float cgl,
                                                       float* __restrict__ adv, float* __restrict__ ret, int T, int N) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
+    const bool want_v = adv != nullptr;
+    GaeBatch<U> b0, b1;
+    gae_load<U>(b0, r, v, done, want_v, T, N, n);
     float a_next = 0.0f;
     float g_next = end_value ? end_value[n] : 0.0f;
-    float v_next = (adv != nullptr) ? __ldcs(v + (size_t)T * N + n) : 0.0f;
-    for (int t1 = T; t1 > 0; t1 -= U) {
-        float rr[U], vv[U];
-        uint8_t dd[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int t = t1 - 1 - u;
-            const bool ok = t >= 0;
-            const size_t i = (size_t)(ok ? t : 0) * N + n;
-            rr[u] = ok ? __ldcs(r + i) : 0.0f;
-            vv[u] = (ok && adv) ? __ldcs(v + i) : 0.0f;
-            dd[u] = (ok && done) ? __ldcs(done + i) : (uint8_t)0;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int t = t1 - 1 - u;
-            if (t < 0) break;
-            const size_t i = (size_t)t * N + n;
-            const bool cut = dd[u] != 0;
-            if (adv) {
-                float vn = cut ? 0.0f : v_next;
-                float delta = (rr[u] + g * vn) - vv[u];
-                float av = (t == T - 1 || cut) ? delta : delta + cgl * a_next;
-                __stcs(adv + i, av);
-                a_next = av;
-                v_next = vv[u];
-            }
-            if (ret) {
-                float gn = cut ? 0.0f : g_next;
-                float G_t = rr[u] + g * gn;
-                __stcs(ret + i, G_t);
-                g_next = G_t;
-            }
-        }
+    float v_next = want_v ? __ldcs(v + (size_t)T * N + n) : 0.0f;
+    for (int t1 = T; t1 > 0; t1 -= 2 * U) {
+        if (t1 - U > 0) gae_load<U>(b1, r, v, done, want_v, t1 - U, N, n);
+        gae_scan<U>(b0, g, cgl, adv, ret, t1, T, N, n, a_next, g_next, v_next);
+        if (t1 - U <= 0) break;
+        if (t1 - 2 * U > 0) gae_load<U>(b0, r, v, done, want_v, t1 - 2 * U, N, n);
+        gae_scan<U>(b1, g, cgl, adv, ret, t1 - U, T, N, n, a_next, g_next, v_next);
     }
 }
 
