@@ -31,6 +31,24 @@ int fail(const std::string& m) { g_err = m; return 1; }
 
 constexpr int kThreads = 128;
 
+using StepKernel = void (*)(DevParams, KArgs);
+
+// Compile-time specialisations of the step kernel for the BASELINE worlds (agar_kernels.cuh, "config views"):
+// <agents, bots, pellets, viruses, food slots, grid, channel flags, ticks>, each with the CTAs-per-SM bound its
+// shared-memory footprint allows on B200.  Any other config runs the RtCfg instantiation.
+using CvCfg1 = StCfg<1, 0, 1000, 0, 64, 64, 7, 4>;    // configs[0]/[2]/[4]: single agent, pellets only
+using CvCfg2 = StCfg<1, 25, 1000, 25, 64, 64, 7, 4>;  // configs[1]: 25 bots + 25 viruses
+using CvCfg4 = StCfg<16, 0, 1000, 0, 64, 64, 7, 4>;   // configs[3]: 16 agents per arena
+
+template <class CV>
+bool matches(const AgarConfig& c, const AgarLayout& L) {
+    typedef typename CV::Layout SL;
+    return c.num_agents == CV::A && c.num_bots == CV::BOTS && c.num_pellets == CV::P && c.num_viruses == CV::V &&
+           c.max_foods == CV::F && c.grid_size == CV::G && c.obs_flags == CV::FLAGS && c.ticks_per_step == CV::TICKS &&
+           c.event_capacity == 0 && L.words == SL::words && L.cell_m == SL::cell_m && L.food_vy == SL::food_vy &&
+           L.agent_done == SL::agent_done && L.tick == SL::tick && L.dyn_begin == SL::dyn_begin;
+}
+
 }  // namespace
 
 struct AgarEnv {
@@ -45,6 +63,8 @@ struct AgarEnv {
     int32_t n_actions = 0;
     size_t smem = 0;
     int min_blocks = 5;  // which agar_step_kernel instantiation to launch
+    StepKernel kernel = nullptr;
+    const char* kernel_name = "";
     int64_t launches = 0;
     // staging for agar_step_host
     float* d_target = nullptr; int32_t* d_act = nullptr; float* d_obs = nullptr;
@@ -61,12 +81,7 @@ size_t obs_elems(const AgarEnv* e) {
 
 int launch(AgarEnv* e, KArgs& a, int n_records, cudaStream_t st) {
     a.n_records = n_records;
-    switch (e->min_blocks) {
-        case 8: agar_step_kernel<kThreads, 8><<<n_records, kThreads, e->smem, st>>>(e->p, a); break;
-        case 7: agar_step_kernel<kThreads, 7><<<n_records, kThreads, e->smem, st>>>(e->p, a); break;
-        case 6: agar_step_kernel<kThreads, 6><<<n_records, kThreads, e->smem, st>>>(e->p, a); break;
-        default: agar_step_kernel<kThreads, 5><<<n_records, kThreads, e->smem, st>>>(e->p, a); break;
-    }
+    e->kernel<<<n_records, kThreads, e->smem, st>>>(e->p, a);
     CUDA_OK(cudaGetLastError());
     e->launches += 1;
     return 0;
@@ -149,10 +164,20 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
         const int v = std::atoi(mb);
         if (v >= 5 && v <= 8) e->min_blocks = v;
     }
-    CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    CUDA_OK(cudaFuncSetAttribute(agar_step_kernel<kThreads, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    const bool generic_only = std::getenv("AGAR_GENERIC_KERNEL") != nullptr;  // tuning/test switch: never specialise
+    if (!generic_only && matches<CvCfg2>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 7, CvCfg2>; e->kernel_name = "cfg2"; }
+    else if (!generic_only && matches<CvCfg1>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 8, CvCfg1>; e->kernel_name = "cfg1"; }
+    else if (!generic_only && matches<CvCfg4>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 8, CvCfg4>; e->kernel_name = "cfg4"; }
+    else {
+        e->kernel_name = "generic";
+        switch (e->min_blocks) {
+            case 8: e->kernel = agar_step_kernel<kThreads, 8, RtCfg>; break;
+            case 7: e->kernel = agar_step_kernel<kThreads, 7, RtCfg>; break;
+            case 6: e->kernel = agar_step_kernel<kThreads, 6, RtCfg>; break;
+            default: e->kernel = agar_step_kernel<kThreads, 5, RtCfg>; break;
+        }
+    }
+    CUDA_OK(cudaFuncSetAttribute(e->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     const size_t state_bytes = (size_t)cfg->num_arenas * p.L.words * sizeof(float);
     CUDA_OK(cudaMalloc(&e->d_state, state_bytes));
     CUDA_OK(cudaMemset(e->d_state, 0, state_bytes));
@@ -389,5 +414,16 @@ int agar_screen_gray(const uint8_t* d_rgb, int64_t n_pixels, void* d_out, int32_
 }
 
 int64_t agar_launch_count(const AgarEnv* e) { return e ? e->launches : 0; }
+
+#ifdef AGAR_PHASE_CLOCKS
+// tuning builds only (not declared in the header): cycles charged to each phase id since the last call
+int agar_debug_phase_clocks(unsigned long long* h_out32) {
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpyFromSymbol(h_out32, g_phase_clocks, sizeof(unsigned long long) * 32));
+    unsigned long long zero[32] = {0};
+    CUDA_OK(cudaMemcpyToSymbol(g_phase_clocks, zero, sizeof(zero)));
+    return 0;
+}
+#endif
 
 }  // extern "C"

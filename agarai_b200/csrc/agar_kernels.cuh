@@ -21,6 +21,20 @@
 #define NONE_I 0x7fffffff
 #define NONE16 0xFFFFu
 
+// Tuning builds only (-DAGAR_PHASE_CLOCKS): thread 0 of every CTA charges the cycles since the previous mark to
+// a phase id; totals are read back with agar_debug_phase_clocks().  Compiled out of the product.
+#ifdef AGAR_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clocks[32];
+__shared__ long long ph_acc[33];  // [32] = time of the previous mark
+#define PHASE_DECL if (threadIdx.x == 0) { for (int i_ = 0; i_ < 32; ++i_) ph_acc[i_] = 0; ph_acc[32] = clock64(); }
+#define PHASE(id) do { if (threadIdx.x == 0) { const long long t_ = clock64(); ph_acc[id] += t_ - ph_acc[32]; ph_acc[32] = t_; } } while (0)
+#define PHASE_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 32; ++i_) if (ph_acc[i_]) atomicAdd(&g_phase_clocks[i_], (unsigned long long)ph_acc[i_]); } while (0)
+#else
+#define PHASE_DECL
+#define PHASE(id) do { } while (0)
+#define PHASE_FLUSH do { } while (0)
+#endif
+
 namespace agar {
 
 struct DevParams {
@@ -60,6 +74,44 @@ struct KArgs {
 };
 
 enum { F_STEP = 1, F_RESET = 2, F_OBS = 4, F_READONLY = 8 };
+
+// ------------------------------------------------------------------------- config views
+// The kernels are templates over a "config view".  RtCfg reads every size and record offset from the kernel
+// parameters (any AgarConfig).  StCfg<...> fixes the sizes of one world at compile time: record offsets and
+// the shared-memory map become immediates of the load/store instructions, loops get constant trip counts and
+// the branches of absent features (viruses, events, unused channels) disappear.  The host launches a StCfg
+// instantiation when the handle's config matches one (the BASELINE worlds), else the RtCfg one; the source
+// is the same, so results are identical (tests/test_gpu_parity.py runs both).
+struct RtCfg {
+    static constexpr bool is_static = false;
+    static constexpr int A = 0, BOTS = 0, P = 0, V = 0, F = 0, G = 0, FLAGS = 0, TICKS = 0, K = 0, KC = 0, C = 0;
+    struct Layout {};
+};
+__host__ __device__ constexpr int cpad4(int n) { return (n + 3) & ~3; }
+template <int A_, int BOTS_, int P_, int V_, int F_, int G_, int FLAGS_, int TICKS_>
+struct StCfg {
+    static constexpr bool is_static = true;
+    static constexpr int A = A_, BOTS = BOTS_, P = P_, V = V_, F = F_, G = G_, FLAGS = FLAGS_, TICKS = TICKS_;
+    static constexpr int K = A_ + BOTS_, KC = K * AGAR_MAX_CELLS;
+    static constexpr int C = ((FLAGS_ >> 0) & 1) + ((FLAGS_ >> 1) & 1) + ((FLAGS_ >> 2) & 1) + ((FLAGS_ >> 3) & 1) + ((FLAGS_ >> 4) & 1);
+    struct Layout {  // agar_spec_layout (include/agar_spec.h) as constants; the host checks them against the handle's layout
+        static constexpr int P_pad = cpad4(P_), V_pad = cpad4(V_), F_pad = cpad4(F_), A_pad = cpad4(A_);
+        static constexpr int num_players = K, cells_total = KC;
+        static constexpr int pellet_x = 0, pellet_y = P_pad, virus_x = 2 * P_pad, virus_y = 2 * P_pad + V_pad;
+        static constexpr int dyn_begin = 2 * P_pad + 2 * V_pad;
+        static constexpr int cell_x = dyn_begin, cell_y = cell_x + KC, cell_ix = cell_y + KC, cell_iy = cell_ix + KC;
+        static constexpr int cell_m = cell_iy + KC, cell_t = cell_m + KC;
+        static constexpr int food_x = cell_t + KC, food_y = food_x + F_pad, food_vx = food_y + F_pad, food_vy = food_vx + F_pad;
+        static constexpr int agent_done = food_vy + F_pad, tick = agent_done + A_pad, episode_steps = tick + 1;
+        static constexpr int dyn_end = tick + 4, words = dyn_end;
+    };
+};
+template <class CV>
+__device__ __forceinline__ decltype(auto) layout_of(const DevParams& p) {
+    if constexpr (CV::is_static) return typename CV::Layout{};
+    else return (p.L);
+}
+#define CV_INT(name, runtime_value) (CV::is_static ? CV::name : (runtime_value))
 
 // ------------------------------------------------------------------------- Philox4x32-10
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -241,47 +293,57 @@ struct Smem {
     int32_t *palive, *pmask;                         // [K_pad]
     float *dirx, *diry, *mass0;                      // [A_pad] (agents only)
     int32_t* pact;                                   // [A_pad]
+    uint8_t* cgrid;                                  // [2][HASH_BINS] alive cells per hash bin, by tick parity (eat-test cull)
     int32_t* rb;                                     // [96] raster: other players' cells in view
     int32_t* sc;                                     // [32] scalars + [32] list-membership bitmask
 };
 enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT, SC_EVCOUNT, SC_RESET, SC_ALLDONE,
-       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NOB, SC_HBUILT, SC_NEX0, SC_COUNT };
+       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NOB, SC_HBUILT, SC_NEX0, SC_BIGCELL, SC_COUNT };
 static_assert(SC_COUNT <= 32, "scalar slots overlap the list-membership bitmask");
 
 __host__ __device__ inline size_t pad4z(size_t n) { return (n + 3) & ~(size_t)3; }
-__host__ __device__ inline size_t gain_words(const AgarLayout& L) {
+template <class LT>
+__host__ __device__ inline size_t gain_words(const LT& L) {
     const size_t a = (size_t)L.cells_total, b = (size_t)L.F_pad + 4;
     return a > b ? a : b;
 }
-__host__ __device__ inline size_t scratch_words(const AgarLayout& L) {
+template <class LT>
+__host__ __device__ inline size_t scratch_words(const LT& L) {
     // hcur | pwin | hits | list, eater (16-bit) | cnt32 | gain
     return HASH_BINS + (size_t)L.P_pad / 2 + HITS_CAP / 2 + (size_t)L.cells_total + (size_t)L.cells_total / 2 + gain_words(L);
 }
-__host__ __device__ inline size_t union_words(const AgarLayout& L, int G) {
+template <class LT>
+__host__ __device__ inline size_t union_words(const LT& L, int G) {
     (void)G;  // the observation needs no shared-memory tile: it is written from registers and patched in place
     return pad4z(scratch_words(L));
 }
-__host__ __device__ inline size_t kpad(const AgarLayout& L) { return pad4z((size_t)L.num_players); }
+template <class LT>
+__host__ __device__ inline size_t kpad(const LT& L) { return pad4z((size_t)L.num_players); }
 
 // persisted hash record: the shared-memory block [hstart | sorted | extras] followed by the header
-__host__ __device__ inline size_t hash_body_words(const AgarLayout& L) {
+template <class LT>
+__host__ __device__ inline size_t hash_body_words(const LT& L) {
     return HASH_BINS + 4 + pad4z((size_t)L.P_pad / 2) + EXTRA_CAP / 2;
 }
-__host__ __device__ inline size_t hash_record_words(const AgarLayout& L) { return hash_body_words(L) + HASH_HDR; }
+template <class LT>
+__host__ __device__ inline size_t hash_record_words(const LT& L) { return hash_body_words(L) + HASH_HDR; }
 
-__host__ __device__ inline size_t smem_bytes(const AgarLayout& L, int G) {
+template <class LT>
+__host__ __device__ inline size_t smem_bytes(const LT& L, int G) {
     size_t w = 0;
     w += (size_t)L.words;                                   // rec
     w += HASH_BINS + 4 + pad4z((size_t)L.P_pad / 2) + EXTRA_CAP / 2 + HASH_HDR + 4 + pad4z((size_t)L.P_pad / 32 + 1);  // hash kept, header, mbarrier
     w += union_words(L, G);                                 // per-tick scratch
     w += (size_t)(L.V_pad + 4);                             // vwin
     w += kpad(L) * 6 + (size_t)L.A_pad * 4;                 // per-player and per-agent arrays
+    w += 2 * HASH_BINS / 4;                                 // cell-count grids
     w += 96;                                                // raster buffers
     w += 64;                                                // scalars + alive-list membership bits
     return w * 4 + 16;
 }
 
-__device__ __forceinline__ Smem carve(float* base, const AgarLayout& L, int G) {
+template <class LT>
+__device__ __forceinline__ Smem carve(float* base, const LT& L, int G) {
     Smem s;
     float* p = base;
     s.rec = p; s.reci = (int32_t*)p; p += L.words;           // words % 4 == 0
@@ -308,6 +370,7 @@ __device__ __forceinline__ Smem carve(float* base, const AgarLayout& L, int G) {
     s.palive = (int32_t*)p; p += kp; s.pmask = (int32_t*)p; p += kp;
     s.dirx = p; p += L.A_pad; s.diry = p; p += L.A_pad; s.mass0 = p; p += L.A_pad;
     s.pact = (int32_t*)p; p += L.A_pad;
+    s.cgrid = (uint8_t*)p; p += 2 * HASH_BINS / 4;
     s.rb = (int32_t*)p; p += 96;
     s.sc = (int32_t*)p; p += 64;
     return s;
@@ -318,23 +381,28 @@ __device__ __noinline__ void ev_push_slow(int* counter, int32_t* events, int cap
     int i = atomicAdd(counter, 1);
     if (i < cap) *reinterpret_cast<int4*>(events + ((size_t)arena * cap + i) * 4) = make_int4(tick, type, x, y);
 }
+template <class CV>
 __device__ __forceinline__ void ev_push(const DevParams& p, const KArgs& a, const Smem& s, int arena, int tick,
                                         int type, int x, int y) {
-    if (p.c.event_capacity > 0) ev_push_slow(&s.sc[SC_EVCOUNT], a.events, p.c.event_capacity, arena, tick, type, x, y);
+    if (!CV::is_static && p.c.event_capacity > 0) ev_push_slow(&s.sc[SC_EVCOUNT], a.events, p.c.event_capacity, arena, tick, type, x, y);
 }
 
 // ----------------------------------------------------------------------------- sub-phases
+template <class CV>
 __device__ __forceinline__ void clear_cell(const DevParams& p, const Smem& s, int g) {
-    s.rec[p.L.cell_x + g] = 0.0f; s.rec[p.L.cell_y + g] = 0.0f; s.rec[p.L.cell_ix + g] = 0.0f;
-    s.rec[p.L.cell_iy + g] = 0.0f; s.rec[p.L.cell_m + g] = 0.0f; s.rec[p.L.cell_t + g] = 0.0f;
+    decltype(auto) L = layout_of<CV>(p);
+    s.rec[L.cell_x + g] = 0.0f; s.rec[L.cell_y + g] = 0.0f; s.rec[L.cell_ix + g] = 0.0f;
+    s.rec[L.cell_iy + g] = 0.0f; s.rec[L.cell_m + g] = 0.0f; s.rec[L.cell_t + g] = 0.0f;
 }
 
 // env.reset() for one arena, in shared memory (reset_arena in the oracle)
 // (out of line, re-deriving the shared-memory map itself: rare path, kept off the hot instruction stream)
+template <class CV>
 __device__ __noinline__ void reset_arena(const DevParams& p, uint32_t gid_lo, uint32_t gid_hi) {
     extern __shared__ __align__(16) float smem_raw[];
-    const Smem s = carve(smem_raw, p.L, p.c.grid_size);
-    const AgarLayout& L = p.L;
+    decltype(auto) L = layout_of<CV>(p);
+    const Smem s = carve(smem_raw, L, CV_INT(G, p.c.grid_size));
+    const int P = CV_INT(P, p.c.num_pellets), V = CV_INT(V, p.c.num_viruses), K = CV_INT(K, p.K);
     const int tid = threadIdx.x, nt = blockDim.x;
     uint32_t tick = (uint32_t)s.reci[L.tick];
     __syncthreads();
@@ -343,16 +411,16 @@ __device__ __noinline__ void reset_arena(const DevParams& p, uint32_t gid_lo, ui
     if (tid == 0) s.reci[L.tick] = (int32_t)tick;
     for (int i = tid; i < L.P_pad; i += nt) {
         float x = -1.0f, y = -1.0f;
-        if (i < p.c.num_pellets) rand_pos(p, gid_lo, gid_hi, (uint32_t)i, AGAR_STREAM_PELLET_INIT, tick, x, y);
+        if (i < P) rand_pos(p, gid_lo, gid_hi, (uint32_t)i, AGAR_STREAM_PELLET_INIT, tick, x, y);
         s.rec[L.pellet_x + i] = x; s.rec[L.pellet_y + i] = y;
     }
     for (int i = tid; i < L.V_pad; i += nt) {
         float x = -1.0f, y = -1.0f;
-        if (i < p.c.num_viruses) rand_pos(p, gid_lo, gid_hi, (uint32_t)i, AGAR_STREAM_VIRUS_INIT, tick, x, y);
+        if (i < V) rand_pos(p, gid_lo, gid_hi, (uint32_t)i, AGAR_STREAM_VIRUS_INIT, tick, x, y);
         s.rec[L.virus_x + i] = x; s.rec[L.virus_y + i] = y;
     }
     for (int i = tid; i < L.F_pad; i += nt) s.rec[L.food_x + i] = -1.0f;
-    for (int k = tid; k < p.K; k += nt) {
+    for (int k = tid; k < K; k += nt) {
         float x, y;
         rand_pos(p, gid_lo, gid_hi, (uint32_t)k, AGAR_STREAM_PLAYER_SPAWN, tick, x, y);
         s.rec[L.cell_x + k * MC] = x; s.rec[L.cell_y + k * MC] = y;
@@ -370,11 +438,12 @@ __device__ __forceinline__ int hash_coord(const DevParams& p, float v) {
 // counting sort of the present pellets into the HASH_W x HASH_W grid (all threads; ends synchronised).
 // Order inside a bin is arbitrary: every consumer reduces with min / integer counts.
 // Out of line: with the hash persisted across steps this runs only after resets and respawn overflows.
+template <class CV>
 __device__ __noinline__ void build_hash(const DevParams& p) {
     extern __shared__ __align__(16) float smem_raw[];
-    const Smem s = carve(smem_raw, p.L, p.c.grid_size);
-    const AgarLayout& L = p.L;
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, P = p.c.num_pellets;
+    decltype(auto) L = layout_of<CV>(p);
+    const Smem s = carve(smem_raw, L, CV_INT(G, p.c.grid_size));
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, P = CV_INT(P, p.c.num_pellets);
     const float* px = s.rec + L.pellet_x; const float* py = s.rec + L.pellet_y;
     for (int i = tid; i < HASH_BINS; i += nt) s.hcur[i] = 0;
     for (int i = tid; i < L.P_pad / 32 + 1; i += nt) s.isx[i] = 0;
@@ -413,14 +482,16 @@ __device__ __noinline__ void build_hash(const DevParams& p) {
 
 // all threads: unordered list of the alive cells' gids, per-player alive masks, "some player has
 // several cells" flag.  SC_NLIST and SC_MULTI must be 0 on entry (a barrier earlier).
+template <class CV>
 __device__ __forceinline__ void build_list(const DevParams& p, const Smem& s) {
-    const AgarLayout& L = p.L;
+    decltype(auto) L = layout_of<CV>(p);
+    const int KC = CV_INT(KC, p.KC);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-    for (int base = 0; base < p.KC; base += nt) {
+    for (int base = 0; base < KC; base += nt) {
         const int g = base + tid;
-        const bool al = g < p.KC && s.rec[L.cell_m + g] > 0.0f;
+        const bool al = g < KC && s.rec[L.cell_m + g] > 0.0f;
         const unsigned b = __ballot_sync(0xffffffffu, al);
-        if (g < p.KC && (lane & 15) == 0) {
+        if (g < KC && (lane & 15) == 0) {
             unsigned hm = (b >> (lane & 16)) & 0xFFFFu;
             s.pmask[g >> 4] = (int)hm;
             if (__popc(hm) >= 2) s.sc[SC_MULTI] = 1;
@@ -501,11 +572,13 @@ __device__ __forceinline__ void count_entity(const DevParams& p, float* __restri
 // occupied bins are patched: count
 // channels (pellets, viruses, foods) by float reductions of 1.0 in global memory, mass channels (own
 // cells, others) by warp 0 with sums taken in entity order.
+template <class CV>
 __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restrict__ obs_arena, bool use_hash) {
-    const AgarLayout& L = p.L;
+    decltype(auto) L = layout_of<CV>(p);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const int hbase = lane & 16, slot = lane & 15;
-    const int G = p.c.grid_size, GG = G * G, A = p.c.num_agents, K = p.K, C = p.C;
+    const int G = CV_INT(G, p.c.grid_size), GG = G * G, A = CV_INT(A, p.c.num_agents), K = CV_INT(K, p.K), C = CV_INT(C, p.C);
+    const int KC = CV_INT(KC, p.KC), obs_flags = CV_INT(FLAGS, p.c.obs_flags);
     const float lim = p.raster_lim;
     const int half = G / 2;
     const float* px = s.rec + L.pellet_x; const float* py = s.rec + L.pellet_y;
@@ -517,11 +590,11 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
     int ch_pel = -1, ch_cells = -1, ch_others = -1, ch_vir = -1, ch_food = -1, sentmask = 0;
     {
         int ch = 0;
-        if (p.c.obs_flags & AGAR_OBS_PELLETS) { ch_pel = ch; sentmask |= 1 << ch; ++ch; }
-        if (p.c.obs_flags & AGAR_OBS_CELLS) { ch_cells = ch; sentmask |= 1 << ch; ++ch; }
-        if (p.c.obs_flags & AGAR_OBS_OTHERS) { ch_others = ch; if (K > 1) sentmask |= 1 << ch; ++ch; }  // no pass without others
-        if (p.c.obs_flags & AGAR_OBS_VIRUSES) { ch_vir = ch; sentmask |= 1 << ch; ++ch; }
-        if (p.c.obs_flags & AGAR_OBS_FOODS) { ch_food = ch; sentmask |= 1 << ch; ++ch; }
+        if (obs_flags & AGAR_OBS_PELLETS) { ch_pel = ch; sentmask |= 1 << ch; ++ch; }
+        if (obs_flags & AGAR_OBS_CELLS) { ch_cells = ch; sentmask |= 1 << ch; ++ch; }
+        if (obs_flags & AGAR_OBS_OTHERS) { ch_others = ch; if (K > 1) sentmask |= 1 << ch; ++ch; }  // no pass without others
+        if (obs_flags & AGAR_OBS_VIRUSES) { ch_vir = ch; sentmask |= 1 << ch; ++ch; }
+        if (obs_flags & AGAR_OBS_FOODS) { ch_food = ch; sentmask |= 1 << ch; ++ch; }
     }
     // centroids of all agents (half-warp per agent; single-cell agents take the one-term form)
     for (int base = (tid & ~31); base < A * MC; base += nt) {  // warp-uniform; warps without a valid lane skip
@@ -539,6 +612,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
         }
     }
     if (tid == 0) s.sc[SC_NOB] = 0;
+    PHASE(17);  // raster: setup + centroids
     // write-out geometry: when 4*nt is a multiple of G a thread keeps its 4 columns and walks rows
     const bool fast = ((4 * nt) % G) == 0;
     const int gy_t = (4 * tid) % G, gx_t = (4 * tid) / G, rstep = (4 * nt) / G;
@@ -551,7 +625,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
         float* out_a = obs_arena + (size_t)a * C * GG;
         // ---- gather: other players' cells in view ----
         if (has && ch_others >= 0) {
-            for (int g = tid; g < p.KC; g += nt) {
+            for (int g = tid; g < KC; g += nt) {
                 const float m = cm[g];
                 if (!(m > 0.0f) || (g >> 4) == a) continue;
                 const float dx = cxs[g] - cx, dy = cys[g] - cy;
@@ -563,6 +637,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                 }
             }
         }
+        PHASE(18);  // raster: barrier + gather others
         // ---- base image of every channel ----
         {
             float4* out4 = reinterpret_cast<float4*>(out_a);
@@ -597,7 +672,9 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                 }
             }
         }
+        PHASE(19);  // raster: base image stores
         __syncthreads();  // the base image is ordered before the patches; the gather list is complete
+        PHASE(20);  // raster: barrier after the stores
         if (has) {
             const int nob = s.sc[SC_NOB];
             // ---- warp 0: own cells and others, sums in entity order, stored over the base image ----
@@ -638,7 +715,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                     // crowded view (more than 32 other cells inside it): one thread adds the masses in (player,
                     // slot) order onto the zeros stored above — the same float sequence as the reference's `+=`
                     float* outc = out_a + (size_t)ch_others * GG;
-                    for (int g = 0; g < p.KC; ++g) {
+                    for (int g = 0; g < KC; ++g) {
                         const float m = cm[g];
                         if (!(m > 0.0f) || (g >> 4) == a) continue;
                         const float dx = cxs[g] - cx, dy = cys[g] - cy;
@@ -651,6 +728,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                     }
                 }
             }
+            PHASE(21);  // raster: mass patches (warp 0)
             // ---- count channels ----
             if (ch_pel >= 0) {
                 float* chan = out_a + (size_t)ch_pel * GG;
@@ -675,7 +753,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                         count_entity(p, chan, px[i], py[i], cx, cy, G, half, lim);
                     }
                 } else {
-                    for (int i = tid; i < p.c.num_pellets; i += nt) {
+                    for (int i = tid; i < CV_INT(P, p.c.num_pellets); i += nt) {
                         const float x = px[i];
                         if (x >= 0.0f) count_entity(p, chan, x, py[i], cx, cy, G, half, lim);
                     }
@@ -684,12 +762,12 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
             if (ch_vir >= 0) {
                 float* chan = out_a + (size_t)ch_vir * GG;
                 const float* ex = s.rec + L.virus_x; const float* ey = s.rec + L.virus_y;
-                for (int i = tid; i < p.c.num_viruses; i += nt) count_entity(p, chan, ex[i], ey[i], cx, cy, G, half, lim);
+                for (int i = tid; i < CV_INT(V, p.c.num_viruses); i += nt) count_entity(p, chan, ex[i], ey[i], cx, cy, G, half, lim);
             }
             if (ch_food >= 0) {
                 float* chan = out_a + (size_t)ch_food * GG;
                 const float* ex = s.rec + L.food_x; const float* ey = s.rec + L.food_y;
-                for (int i = tid; i < p.c.max_foods; i += nt) {
+                for (int i = tid; i < CV_INT(F, p.c.max_foods); i += nt) {
                     const float x = ex[i];
                     if (x >= 0.0f) count_entity(p, chan, x, ey[i], cx, cy, G, half, lim);
                 }
@@ -705,14 +783,15 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
 
 // Virus pops of one tick: a cell pops on the lowest virus it won; pops inside a
 // player are sequential in slot order.  All threads; ends synchronised.  Out of line: rare.
+template <class CV>
 __device__ __noinline__ void virus_pops(const DevParams& p, const KArgs& a, int arena, int tk, uint32_t tick,
                                         uint32_t gid_lo, uint32_t gid_hi) {
     extern __shared__ __align__(16) float smem_raw[];
-    const AgarLayout& L = p.L;
+    decltype(auto) L = layout_of<CV>(p);
     const AgarConfig& c = p.c;
-    const Smem s = carve(smem_raw, L, c.grid_size);
+    const Smem s = carve(smem_raw, L, CV_INT(G, c.grid_size));
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int K = p.K, V = c.num_viruses;
+    const int K = CV_INT(K, p.K), V = CV_INT(V, c.num_viruses);
     float* cx = s.rec + L.cell_x; float* cy = s.rec + L.cell_y; float* cix = s.rec + L.cell_ix;
     float* ciy = s.rec + L.cell_iy; float* cm = s.rec + L.cell_m; float* ct = s.rec + L.cell_t;
     float* vx = s.rec + L.virus_x; float* vy = s.rec + L.virus_y;
@@ -737,11 +816,12 @@ __device__ __noinline__ void virus_pops(const DevParams& p, const KArgs& a, int 
             if (v == NONE16) continue;
             s.eater[g] = NONE16;
             float m1 = cm[g] + c.virus_mass;
+            if (!(m1 * c.r2_per_mass < p.hash_bs * p.hash_bs)) s.sc[SC_BIGCELL] = 1;  // eat-test cull off
             int nfree = 0;
 #pragma unroll 1
             for (int q = 0; q < MC; ++q) nfree += (cm[k * MC + q] == 0.0f) ? 1 : 0;
             int np = nfree < c.pop_pieces ? nfree : c.pop_pieces;
-            ev_push(p, a, s, arena, tk, AGAR_EV_VIRUS_POP, g, v);
+            ev_push<CV>(p, a, s, arena, tk, AGAR_EV_VIRUS_POP, g, v);
             if (np > 0) {
                 const float DX[16] = AGAR_DIR16_X; const float DY[16] = AGAR_DIR16_Y;
                 float keep = m1 * 0.5f;
@@ -756,7 +836,7 @@ __device__ __noinline__ void virus_pops(const DevParams& p, const KArgs& a, int 
                     cx[d] = gx; cy[d] = gy;
                     cix[d] = DX[j] * c.pop_speed; ciy[d] = DY[j] * c.pop_speed;
                     cm[d] = piece; ct[d] = c.merge_delay;
-                    ev_push(p, a, s, arena, tk, AGAR_EV_POP_PIECE, g, d);
+                    ev_push<CV>(p, a, s, arena, tk, AGAR_EV_POP_PIECE, g, d);
                     if (!(atomicOr(&inl[d >> 5], 1 << (d & 31)) & (1 << (d & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = (uint16_t)d;
                 }
                 s.sc[SC_MULTI] = 1;
@@ -786,20 +866,22 @@ __device__ __noinline__ void virus_pops(const DevParams& p, const KArgs& a, int 
 //   rewards/dones | B | write back | raster.
 // kMinBlocks is chosen by the host from the shared-memory footprint (CTAs that fit per SM) so that the
 // register budget never becomes the occupancy limit: 5 -> <=100 regs, 6 -> <=80, 7 -> <=72.
-template <int kThreads, int kMinBlocks>
+template <int kThreads, int kMinBlocks, class CV>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const __grid_constant__ DevParams p,
                                                                const __grid_constant__ KArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
-    const AgarLayout& L = p.L;
+    decltype(auto) L = layout_of<CV>(p);
     const AgarConfig& c = p.c;
-    const Smem s = carve(smem_raw, L, c.grid_size);
+    const int G = CV_INT(G, c.grid_size), P = CV_INT(P, c.num_pellets), TICKS = CV_INT(TICKS, c.ticks_per_step);
+    const Smem s = carve(smem_raw, L, G);
     const int tid = threadIdx.x, nt = kThreads, lane = tid & 31;
     const int hbase = lane & 16, slot = lane & 15;
     const int arena = blockIdx.x;
-    const int A = c.num_agents, K = p.K, KC = p.KC, V = c.num_viruses, F = c.max_foods;
+    const int A = CV_INT(A, c.num_agents), K = CV_INT(K, p.K), KC = CV_INT(KC, p.KC), V = CV_INT(V, c.num_viruses), F = CV_INT(F, c.max_foods);
     const uint64_t gid64 = (uint64_t)(c.arena_id_base + arena);
     const uint32_t gid_lo = (uint32_t)gid64, gid_hi = (uint32_t)(gid64 >> 32);
     const float r2pm = c.r2_per_mass, arena_size = c.arena_size;
+    const float bs2 = p.hash_bs * p.hash_bs;  // a cell with radius^2 >= bs2 switches the eat-test cull off
     float* cx = s.rec + L.cell_x; float* cy = s.rec + L.cell_y; float* cix = s.rec + L.cell_ix;
     float* ciy = s.rec + L.cell_iy; float* cm = s.rec + L.cell_m; float* ct = s.rec + L.cell_t;
     float* px = s.rec + L.pellet_x; float* py = s.rec + L.pellet_y;
@@ -808,13 +890,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     float* grec = a.state + (size_t)arena * L.words;  // write target
     int32_t* inl = s.sc + 32;                         // bitmask of gids present in the alive list (sc[0..31] are scalars)
 
+    PHASE_DECL
     // ---- stage the record (and the persisted pellet hash) with TMA bulk copies ----
-    int32_t* ghash = a.hash ? a.hash + (size_t)arena * p.hash_words : nullptr;
+    const int hash_words = CV::is_static ? (int)hash_record_words(L) : p.hash_words;
+    int32_t* ghash = a.hash ? a.hash + (size_t)arena * hash_words : nullptr;
     const bool load_hash = (a.flags & F_STEP) && ghash;
     if (tid == 0) mbar_init(s.mbar, 1);
     __syncthreads();
     if (tid == 0) {
-        const uint32_t rec_bytes = (uint32_t)L.words * 4u, hash_bytes = load_hash ? (uint32_t)p.hash_words * 4u : 0u;
+        const uint32_t rec_bytes = (uint32_t)L.words * 4u, hash_bytes = load_hash ? (uint32_t)hash_words * 4u : 0u;
         mbar_expect_tx(s.mbar, rec_bytes + hash_bytes);
         bulk_g2s(s.rec, a.src_state + (size_t)arena * L.words, rec_bytes, s.mbar);
         if (load_hash) bulk_g2s(s.hstart, ghash, hash_bytes, s.mbar);
@@ -823,6 +907,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         for (int i = tid; i < KC / 2; i += nt) { s.cnt32[i] = 0u; reinterpret_cast<uint32_t*>(s.eater)[i] = 0xFFFFFFFFu; }
         for (int i = tid; i < (int)gain_words(L); i += nt) s.gain[i] = 0.0f;
         if (tid < 64) s.sc[tid] = 0;
+        for (int i = tid; i < 2 * HASH_BINS / 4; i += nt) reinterpret_cast<uint32_t*>(s.cgrid)[i] = 0u;
         if (a.flags & F_STEP) {
             for (int i = tid; i < L.P_pad / 2; i += nt) reinterpret_cast<uint32_t*>(s.pwin)[i] = 0xFFFFFFFFu;
             for (int i = tid; i < L.P_pad / 32 + 1; i += nt) s.isx[i] = 0;
@@ -836,26 +921,28 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
 
     bool static_dirty = false;  // whole record must be written back (after a reset)
     if (a.flags & F_RESET) {
-        if (!a.reset_mask || a.reset_mask[arena]) { reset_arena(p, gid_lo, gid_hi); static_dirty = true; }
+        if (!a.reset_mask || a.reset_mask[arena]) { reset_arena<CV>(p, gid_lo, gid_hi); static_dirty = true; }
     }
 
     if (a.flags & F_STEP) {
         const uint32_t tick0 = (uint32_t)s.reci[L.tick];
+        PHASE(0);  // staging
         // ---- pellet hash (persisted across steps, rebuilt when stale), alive list ----
         if (load_hash && hhdr.x == p.hash_epoch) {
             const int nex = min(hhdr.y, EXTRA_CAP);
             if (tid < nex) { const int i = s.extras[tid]; atomicOr(&s.isx[i >> 5], 1 << (i & 31)); }
             if (tid == 0) { s.sc[SC_NEXTRAS] = nex; s.sc[SC_NEX0] = nex; s.sc[SC_HASHOK] = 1; }
         } else {
-            build_hash(p);
+            build_hash<CV>(p);
         }
-        build_list(p, s);
+        build_list<CV>(p, s);
         for (int base = 0; base < KC; base += nt) {  // membership bits of the list (one word per warp chunk)
             const int g = base + tid;
             const unsigned b = __ballot_sync(0xffffffffu, g < KC && cm[g] > 0.0f);
             if (lane == 0 && g < KC) inl[g >> 5] = (int)b;
         }
         __syncthreads();
+        PHASE(1);  // hash check/build, list
         // ---- players: bot respawn, centroid and mass of single-cell players (thread per player) ----
         for (int k = tid; k < K; k += nt) {
             unsigned pm = (unsigned)s.pmask[k];
@@ -864,7 +951,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 float x, y;
                 rand_pos(p, gid_lo, gid_hi, (uint32_t)k, AGAR_STREAM_PLAYER_SPAWN, tick0, x, y);
                 cx[g] = x; cy[g] = y; cm[g] = c.start_mass;  // the other fields of a dead player's slots are 0
-                ev_push(p, a, s, arena, 0, AGAR_EV_RESPAWN, k, 0);
+                ev_push<CV>(p, a, s, arena, 0, AGAR_EV_RESPAWN, k, 0);
                 pm = 1u; s.pmask[k] = 1;
                 if (!(atomicOr(&inl[g >> 5], 1 << (g & 31)) & (1 << (g & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = (uint16_t)g;
             }
@@ -919,6 +1006,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             if (act == AGAR_ACT_FEED) s.sc[SC_ANYFEED] = 1;
             if (act == AGAR_ACT_SPLIT) s.sc[SC_ANYSPLIT] = 1;
         }
+        PHASE(2);  // players, multi, agent actions
         // ---- bots: nearest pellet in the square sense window, else the roam way-point.  Four lanes
         //      per bot search the 3x3 bins around it; the result is final when it is closer than the
         //      nearest unsearched bin edge, otherwise the whole window is searched ----
@@ -989,6 +1077,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             }
         }
         __syncthreads();
+        PHASE(3);  // bots
         // ---- split: i-th eligible cell -> i-th free slot (ballot ranks inside the half-warp) ----
         if (s.sc[SC_ANYSPLIT]) {
             for (int base = (tid & ~31); base < A * MC; base += nt) {
@@ -1007,7 +1096,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     cx[d] = cx[g]; cy[d] = cy[g];
                     cix[d] = s.dirx[k] * c.split_speed; ciy[d] = s.diry[k] * c.split_speed;
                     cm[d] = halfm; ct[d] = c.merge_delay;
-                    ev_push(p, a, s, arena, 0, AGAR_EV_SPLIT, g, d);
+                    ev_push<CV>(p, a, s, arena, 0, AGAR_EV_SPLIT, g, d);
                     s.sc[SC_MULTI] = 1;
                     if (!(atomicOr(&inl[d >> 5], 1 << (d & 31)) & (1 << (d & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = (uint16_t)d;
                 }
@@ -1041,7 +1130,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     fx[f] = clampf(cx[g] + s.dirx[k] * off, 0.0f, arena_size);
                     fy[f] = clampf(cy[g] + s.diry[k] * off, 0.0f, arena_size);
                     fvx[f] = s.dirx[k] * c.feed_speed; fvy[f] = s.diry[k] * c.feed_speed;
-                    ev_push(p, a, s, arena, 0, AGAR_EV_FEED, g, f);
+                    ev_push<CV>(p, a, s, arena, 0, AGAR_EV_FEED, g, f);
                 }
                 used += __popc(b);
             }
@@ -1050,9 +1139,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         }
         __syncthreads();
 
-        for (int tk = 0; tk < c.ticks_per_step; ++tk) {
+        PHASE(4);  // split, feed
+        for (int tk = 0; tk < TICKS; ++tk) {
             const uint32_t tick = tick0 + (uint32_t)tk;
-            if (s.sc[SC_REBUILD]) build_hash(p);  // too many respawns since the last build (uniform)
+            if (s.sc[SC_REBUILD]) build_hash<CV>(p);
+            PHASE(5);  // in-tick rebuild  // too many respawns since the last build (uniform)
             // ---- motion + pellet query: four lanes per alive cell.  All four evaluate the motion (lane 0
             //      stores it) and then share the scan of the hash runs under the cell's padded bounding
             //      box and of the respawn list.  A pellet whose centre lies inside the disc is claimed
@@ -1061,6 +1152,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 const int n = s.sc[SC_NLIST];
                 const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
                 const int l4 = lane & 3;
+                uint32_t* cg32 = reinterpret_cast<uint32_t*>(s.cgrid + (tk & 1) * HASH_BINS);
                 for (int qb = (tid >> 5) * 8; qb < n; qb += nt >> 2) {  // 8 cells per warp pass, warp-uniform
                     const int q = qb + (lane >> 2);
                     const int g = q < n ? s.list[q] : s.list[0];
@@ -1084,6 +1176,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     if (l4 == 0) {
                         cx[g] = x; cy[g] = y; cix[g] = ix; ciy[g] = iy;
                         if (t > 0.0f) ct[g] = t - 1.0f;
+                        // register the cell in this tick's cell-count grid (one byte per hash bin; a carry out of a
+                        // byte only makes a neighbour look occupied, which is the safe side)
+                        const int b = hash_coord(p, y) * HASH_W + hash_coord(p, x);
+                        atomicAdd(cg32 + (b >> 2), 1u << ((b & 3) * 8));
+                        if (!(r2 < bs2)) s.sc[SC_BIGCELL] = 1;
                     }
                     const float rp = r * 1.001f + 0.01f;
                     const int bx0 = hash_coord(p, x - rp), bx1 = hash_coord(p, x + rp);
@@ -1112,20 +1209,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 for (int v = tid; v < V; v += nt) s.vwin[v] = NONE_I;
             }
             __syncthreads();
+            PHASE(6);  // motion + query (+ barrier)
+            // the other parity's cell-count grid was last read in the previous tick: clear it for the next one
+            if (tid < HASH_BINS / 4) reinterpret_cast<uint32_t*>(s.cgrid + ((tk + 1) & 1) * HASH_BINS)[tid] = 0u;
             const int nh = s.sc[SC_NHITS];                // block-uniform from here on
             const bool food_any = s.sc[SC_FOODANY] != 0;
             const bool gains = nh > 0 || food_any;        // some mass changes this tick before the eat test
             // ---- resolve the claimed pellets: winner = lowest gid (atomicMin), respawn by Philox ----
             if (nh > 0) {
                 const bool listed = nh <= HITS_CAP;  // else the list overflowed: every pellet's winner slot is examined
-                const int nscan = listed ? nh : c.num_pellets;
+                const int nscan = listed ? nh : P;
                 for (int h = tid; h < nscan; h += nt) {
                     const int i = listed ? (int)s.hits[h] : h;
                     const int g = s.pwin[i];
                     if (g == NONE16) continue;
                     s.pwin[i] = NONE16;
                     cnt_inc(s.cnt32, g);
-                    ev_push(p, a, s, arena, tk, AGAR_EV_PELLET_EATEN, g, i);
+                    ev_push<CV>(p, a, s, arena, tk, AGAR_EV_PELLET_EATEN, g, i);
                     float nx = -1.0f, ny = -1.0f;
                     if (c.pellet_regen) {
                         rand_pos(p, gid_lo, gid_hi, (uint32_t)i, AGAR_STREAM_PELLET_RESPAWN, tick, nx, ny);
@@ -1145,7 +1245,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 for (int q = tid; q < n; q += nt) {
                     const int g = s.list[q];
                     const int e = cnt_get(s.cnt32, g);
-                    if (e) { cm[g] = cm[g] + (float)e * c.pellet_mass; cnt_clear(s.cnt32, g); }
+                    if (e) {
+                        const float m = cm[g] + (float)e * c.pellet_mass;
+                        cm[g] = m; cnt_clear(s.cnt32, g);
+                        if (!(m * r2pm < bs2)) s.sc[SC_BIGCELL] = 1;
+                    }
                 }
                 __syncthreads();
                 for (int f = tid; f < F; f += nt) {
@@ -1165,17 +1269,24 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     }
                     if (best != NONE_I) {
                         cnt_inc(s.cnt32, best);
-                        ev_push(p, a, s, arena, tk, AGAR_EV_FOOD_EATEN, best, f);
+                        ev_push<CV>(p, a, s, arena, tk, AGAR_EV_FOOD_EATEN, best, f);
                         fx[f] = -1.0f; fy[f] = 0.0f; fvx[f] = 0.0f; fvy[f] = 0.0f;
                     }
                 }
                 __syncthreads();
             }
+            PHASE(7);  // resolve, foods
             // cell-eats-cell test (different players, pre-phase snapshot): four lanes per prey, each
             // scanning a quarter of the possible eaters; the lowest gid wins
+            // Cull: an eater holds the prey's centre, so it is closer than its own radius; while every radius is
+            // below the hash bin size (SC_BIGCELL == 0) it sits in one of the 3x3 bins around the prey.  The
+            // motion phase counted the alive cells per bin, so a prey whose neighbourhood holds no other cell
+            // skips the scan (cells made by a virus pop after the count share their parent's player and bin).
             auto eat_test = [&]() {
                 const int n = s.sc[SC_NLIST];
                 const int l4 = lane & 3;
+                const bool cull = s.sc[SC_BIGCELL] == 0;  // block-uniform
+                const uint8_t* cg = s.cgrid + (tk & 1) * HASH_BINS;
                 for (int qb = (tid >> 5) * 8; qb < n; qb += nt >> 2) {  // 8 preys per warp pass, warp-uniform
                     const int q = qb + (lane >> 2);
                     const int j = q < n ? s.list[q] : s.list[0];
@@ -1183,7 +1294,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     const float need = mj * c.eat_ratio, x = cx[j], y = cy[j];
                     const int kj = j >> 4;
                     int best = NONE_I;
-                    if (mj > 0.0f) {
+                    bool cand = mj > 0.0f;
+                    if (cull) {
+                        int tot = 0;
+                        const int bx = hash_coord(p, x), row = hash_coord(p, y) - 1 + l4;
+                        if (cand && l4 < 3 && row >= 0 && row < HASH_W) {
+                            const uint8_t* rp = cg + row * HASH_W;
+                            tot = (int)rp[bx] + (bx > 0 ? (int)rp[bx - 1] : 0) + (bx < HASH_W - 1 ? (int)rp[bx + 1] : 0);
+                        }
+                        tot += __shfl_xor_sync(FULL, tot, 1);
+                        tot += __shfl_xor_sync(FULL, tot, 2);
+                        cand = tot > 1;  // the prey itself is counted
+                    }
+                    if (!__any_sync(FULL, cand)) continue;  // warp-uniform
+                    if (cand) {
 #pragma unroll 4
                         for (int qi = l4; qi < n; qi += 4) {
                             const int i = s.list[qi];
@@ -1207,7 +1331,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     const int g = s.list[q];
                     float m = cm[g];
                     const int e = cnt_get(s.cnt32, g);
-                    if (e) { m = m + (float)e * unit; cm[g] = m; cnt_clear(s.cnt32, g); }
+                    if (e) {
+                        m = m + (float)e * unit; cm[g] = m; cnt_clear(s.cnt32, g);
+                        if (!(m * r2pm < bs2)) s.sc[SC_BIGCELL] = 1;
+                    }
                     if (V > 0 && m >= c.virus_pop_mass) {
                         const float r2 = m * r2pm, x = cx[g], y = cy[g];
                         for (int v = 0; v < V; ++v) {
@@ -1219,6 +1346,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             }
             if (tid == 0 && gains) { s.sc[SC_NHITS] = 0; s.sc[SC_FOODANY] = 0; }  // a barrier follows whenever gains
             if (gains && K > 1) __syncthreads();  // the eat test reads the updated masses
+            PHASE(8);  // apply gains, virus claims
             // ---- cell eats cell (one code site).  It runs speculatively before the virus pops are known; a
             //      pop (rare) changes masses, voids the result and the test is taken again ----
             for (bool again = true; again;) {
@@ -1226,10 +1354,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 if (gains || V > 0 || K > 1) __syncthreads();
                 again = false;
                 if (V > 0 && s.sc[SC_ANYVHIT]) {  // block-uniform, rare: out of line
-                    virus_pops(p, a, arena, tk, tick, gid_lo, gid_hi);
+                    virus_pops<CV>(p, a, arena, tk, tick, gid_lo, gid_hi);
                     again = K > 1;
                 }
             }
+            PHASE(9);  // eat test (+ pops) + barrier
             if (K > 1) {
                 if (s.sc[SC_ANYEAT]) {
                     const int n = s.sc[SC_NLIST];
@@ -1242,7 +1371,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                                 int src = __ffs(mask) - 1;
                                 if (lane == src) {
                                     s.gain[w] = s.gain[w] + cm[j];
-                                    ev_push(p, a, s, arena, tk, AGAR_EV_CELL_EATEN, w, j);
+                                    ev_push<CV>(p, a, s, arena, tk, AGAR_EV_CELL_EATEN, w, j);
                                 }
                                 __syncwarp();
                                 mask &= mask - 1;
@@ -1252,7 +1381,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     __syncthreads();
                     for (int q = tid; q < n; q += nt) {
                         const int g = s.list[q];
-                        if (s.eater[g] != NONE16) { clear_cell(p, s, g); s.eater[g] = NONE16; }  // eaten: forfeits its gains
+                        if (s.eater[g] != NONE16) { clear_cell<CV>(p, s, g); s.eater[g] = NONE16; }  // eaten: forfeits its gains
                         else if (s.gain[g] > 0.0f) cm[g] = cm[g] + s.gain[g];
                         s.gain[g] = 0.0f;
                     }
@@ -1260,6 +1389,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     __syncthreads();
                 }
             }
+            PHASE(10);  // eat apply
             // ---- merge own cells whose timers ran out (half-warp per player, shuffles) ----
             if (s.sc[SC_MULTI]) {
                 for (int base = (tid & ~31); base < KC; base += nt) {
@@ -1294,8 +1424,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                         if (rq == slot && q != slot) acc = acc + mq;
                     }
                     if (root != slot) {
-                        ev_push(p, a, s, arena, tk, AGAR_EV_MERGE, (g & ~15) + root, g);
-                        clear_cell(p, s, g);
+                        ev_push<CV>(p, a, s, arena, tk, AGAR_EV_MERGE, (g & ~15) + root, g);
+                        clear_cell<CV>(p, s, g);
                     } else if (acc != m) {
                         cm[g] = acc;
                     }
@@ -1304,6 +1434,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             }
         }
 
+        PHASE(11);  // merge (last tick only; earlier ticks charge it to the rebuild slot)
         // ---- rewards / dones ----
         for (int base = (tid & ~31); base < A * MC; base += nt) {
             const int g = base + lane, k = g >> 4;
@@ -1316,7 +1447,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 float rw = was ? 0.0f : after - s.mass0[k];
                 if (!was && !alive) {
                     s.reci[L.agent_done + k] = 1;
-                    ev_push(p, a, s, arena, c.ticks_per_step, AGAR_EV_DEATH, k, 0);
+                    ev_push<CV>(p, a, s, arena, TICKS, AGAR_EV_DEATH, k, 0);
                 }
                 int d = s.reci[L.agent_done + k];
                 a.reward[(size_t)arena * A + k] = rw;
@@ -1325,17 +1456,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             }
         }
         if (tid == 0) {
-            s.reci[L.tick] = (int32_t)(tick0 + (uint32_t)c.ticks_per_step);
+            s.reci[L.tick] = (int32_t)(tick0 + (uint32_t)TICKS);
             s.reci[L.episode_steps] += 1;
         }
         __syncthreads();
         if (c.auto_reset && !s.sc[SC_ALLDONE]) {
-            reset_arena(p, gid_lo, gid_hi); static_dirty = true;
+            reset_arena<CV>(p, gid_lo, gid_hi); static_dirty = true;
             if (tid == 0) s.sc[SC_HASHOK] = 0;  // pellets were redrawn: the raster scans them all
         }
+        PHASE(12);  // rewards, auto reset
         // ---- persist the pellet hash for the next step ----
         if (a.hash && !(a.flags & F_READONLY)) {
-            int4* gh = reinterpret_cast<int4*>(a.hash + (size_t)arena * p.hash_words);
+            int4* gh = reinterpret_cast<int4*>(a.hash + (size_t)arena * hash_words);
             const int body4 = (int)hash_body_words(L) / 4, ex4 = (HASH_BINS + 4 + (int)pad4z((size_t)L.P_pad / 2)) / 4;
             const int4* src = reinterpret_cast<const int4*>(s.hstart);
             const bool ok = s.sc[SC_HASHOK] != 0;
@@ -1349,9 +1481,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             if (tid == 0 && (stale || s.sc[SC_HBUILT] || nexn != s.sc[SC_NEX0] || hhdr.x != p.hash_epoch))
                 gh[body4] = make_int4(stale ? 0 : p.hash_epoch, nexn, 0, 0);
         }
-        if (c.event_capacity > 0 && tid == 0) a.ev_counts[arena] = s.sc[SC_EVCOUNT];
+        if (!CV::is_static && c.event_capacity > 0 && tid == 0) a.ev_counts[arena] = s.sc[SC_EVCOUNT];
     }
 
+    PHASE(13);  // persist hash
     // ---- write back: one bulk store of the rewritten part (the whole record after a reset) ----
     if (!(a.flags & F_READONLY) && (a.flags & (F_STEP | F_RESET))) {
         const int w0 = static_dirty ? 0 : L.dyn_begin;  // dyn_begin % 4 == 0
@@ -1362,13 +1495,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             bulk_commit();
         }
     }
+    PHASE(14);  // write back
     // ---- observations ----
     if ((a.flags & F_OBS) && a.obs) {
         __syncthreads();
-        const int GG = c.grid_size * c.grid_size;
-        raster_arena(p, s, a.obs + (size_t)arena * A * p.C * GG, s.sc[SC_HASHOK] != 0 && s.sc[SC_REBUILD] == 0);
+        const int GG = G * G;
+        raster_arena<CV>(p, s, a.obs + (size_t)arena * A * CV_INT(C, p.C) * GG, s.sc[SC_HASHOK] != 0 && s.sc[SC_REBUILD] == 0);
     }
+    PHASE(15);  // raster
     if (tid == 0) bulk_wait_read0();  // the bulk store must have read the record before the CTA exits
+    PHASE(16);  // wait for the bulk store
+    PHASE_FLUSH;
 }
 
 // -------------------------------------------------------------------------------- GAE

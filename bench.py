@@ -275,9 +275,14 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--world", default="cfg2", choices=sorted(WORLDS), help="BASELINE.json world (default: the headline cfg2)")
+    ap.add_argument("--set", action="append", default=[], metavar="FIELD=VALUE",
+                    help="tuning experiments only: override a world field (e.g. ticks_per_step=8); the line says so in config")
     args = ap.parse_args()
     global WORLD
-    WORLD = WORLDS[args.world]
+    WORLD = dict(WORLDS[args.world])
+    for kv in args.set:
+        k, v = kv.split("=")
+        WORLD[k] = type(WORLDS[args.world].get(k, 0))(float(v))
     if args.impl == "reference":
         run_reference(args)
     else:

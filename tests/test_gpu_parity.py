@@ -524,3 +524,35 @@ def test_ram_env_id_and_full_observation_view(oracle):
     benv = ab.make("agario-ram-v0", num_envs=16, seed=4, **kw)  # batched: torch tensors
     assert tuple(benv.reset().shape) == (16, 2, 580)
     benv.close()
+
+
+@pytest.mark.parametrize("world", ["cfg1", "cfg2", "cfg4"])
+def test_compile_time_specialised_kernels_match_oracle_and_generic_kernel(oracle, world):
+    """The BASELINE worlds run step kernels whose sizes and record offsets are compile-time constants
+    (agar_kernels.cuh "config views").  Same source as the generic kernel: states, observations, rewards and
+    dones must equal the oracle's, and the generic kernel's, bit for bit."""
+    import agarai_b200 as ab
+    import bench
+    kw = dict(bench.WORLDS[world], num_arenas=24, auto_reset=1)
+    genv, oenv = make_pair(oracle, seed=31, **kw)                   # event_capacity 0 -> specialised instantiation
+    os.environ["AGAR_GENERIC_KERNEL"] = "1"
+    try:
+        renv = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=31)  # same world on the runtime-config kernel
+    finally:
+        del os.environ["AGAR_GENERIC_KERNEL"]
+    rng = np.random.default_rng(8)
+    N, A = 24, kw["num_agents"]
+    g0 = genv.reset(); r0 = renv.reset()
+    assert np.array_equal(g0.cpu().numpy(), oenv.reset()) and torch.equal(g0, r0)
+    for t in range(80):
+        xy, act = random_actions(rng, N, A, (0, 1, 2), 0.4)
+        txy, tact = torch.from_numpy(xy).cuda(), torch.from_numpy(act).cuda()
+        g_o, g_r, g_d, _ = genv.step(txy, tact)
+        r_o, r_r, r_d, _ = renv.step(txy, tact)
+        o_o, o_r, o_d = oenv.step(xy, act)
+        assert_same_state(genv, oenv, f"{world} step {t}")
+        assert np.array_equal(g_o.cpu().numpy().view(np.int32), o_o.view(np.int32)), f"obs step {t}"
+        assert np.array_equal(g_r.cpu().numpy().view(np.int32), o_r.view(np.int32)) and np.array_equal(g_d.cpu().numpy(), o_d)
+        assert torch.equal(g_o, r_o) and torch.equal(g_r, r_r) and torch.equal(g_d, r_d)
+        assert torch.equal(genv.get_state(), renv.get_state())
+    genv.close(); renv.close()
