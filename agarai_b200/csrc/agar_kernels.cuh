@@ -293,12 +293,11 @@ struct Smem {
     int32_t *palive, *pmask;                         // [K_pad]
     float *dirx, *diry, *mass0;                      // [A_pad] (agents only)
     int32_t* pact;                                   // [A_pad]
-    uint8_t* cgrid;                                  // [2][HASH_BINS] alive cells per hash bin, by tick parity (eat-test cull)
     int32_t* rb;                                     // [96] raster: other players' cells in view
     int32_t* sc;                                     // [32] scalars + [32] list-membership bitmask
 };
 enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT, SC_EVCOUNT, SC_RESET, SC_ALLDONE,
-       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NOB, SC_HBUILT, SC_NEX0, SC_BIGCELL, SC_COUNT };
+       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NOB, SC_HBUILT, SC_NEX0, SC_COUNT };
 static_assert(SC_COUNT <= 32, "scalar slots overlap the list-membership bitmask");
 
 __host__ __device__ inline size_t pad4z(size_t n) { return (n + 3) & ~(size_t)3; }
@@ -336,7 +335,6 @@ __host__ __device__ inline size_t smem_bytes(const LT& L, int G) {
     w += union_words(L, G);                                 // per-tick scratch
     w += (size_t)(L.V_pad + 4);                             // vwin
     w += kpad(L) * 6 + (size_t)L.A_pad * 4;                 // per-player and per-agent arrays
-    w += 2 * HASH_BINS / 4;                                 // cell-count grids
     w += 96;                                                // raster buffers
     w += 64;                                                // scalars + alive-list membership bits
     return w * 4 + 16;
@@ -370,7 +368,6 @@ __device__ __forceinline__ Smem carve(float* base, const LT& L, int G) {
     s.palive = (int32_t*)p; p += kp; s.pmask = (int32_t*)p; p += kp;
     s.dirx = p; p += L.A_pad; s.diry = p; p += L.A_pad; s.mass0 = p; p += L.A_pad;
     s.pact = (int32_t*)p; p += L.A_pad;
-    s.cgrid = (uint8_t*)p; p += 2 * HASH_BINS / 4;
     s.rb = (int32_t*)p; p += 96;
     s.sc = (int32_t*)p; p += 64;
     return s;
@@ -816,7 +813,6 @@ __device__ __noinline__ void virus_pops(const DevParams& p, const KArgs& a, int 
             if (v == NONE16) continue;
             s.eater[g] = NONE16;
             float m1 = cm[g] + c.virus_mass;
-            if (!(m1 * c.r2_per_mass < p.hash_bs * p.hash_bs)) s.sc[SC_BIGCELL] = 1;  // eat-test cull off
             int nfree = 0;
 #pragma unroll 1
             for (int q = 0; q < MC; ++q) nfree += (cm[k * MC + q] == 0.0f) ? 1 : 0;
@@ -881,7 +877,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     const uint64_t gid64 = (uint64_t)(c.arena_id_base + arena);
     const uint32_t gid_lo = (uint32_t)gid64, gid_hi = (uint32_t)(gid64 >> 32);
     const float r2pm = c.r2_per_mass, arena_size = c.arena_size;
-    const float bs2 = p.hash_bs * p.hash_bs;  // a cell with radius^2 >= bs2 switches the eat-test cull off
     float* cx = s.rec + L.cell_x; float* cy = s.rec + L.cell_y; float* cix = s.rec + L.cell_ix;
     float* ciy = s.rec + L.cell_iy; float* cm = s.rec + L.cell_m; float* ct = s.rec + L.cell_t;
     float* px = s.rec + L.pellet_x; float* py = s.rec + L.pellet_y;
@@ -907,7 +902,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         for (int i = tid; i < KC / 2; i += nt) { s.cnt32[i] = 0u; reinterpret_cast<uint32_t*>(s.eater)[i] = 0xFFFFFFFFu; }
         for (int i = tid; i < (int)gain_words(L); i += nt) s.gain[i] = 0.0f;
         if (tid < 64) s.sc[tid] = 0;
-        for (int i = tid; i < 2 * HASH_BINS / 4; i += nt) reinterpret_cast<uint32_t*>(s.cgrid)[i] = 0u;
         if (a.flags & F_STEP) {
             for (int i = tid; i < L.P_pad / 2; i += nt) reinterpret_cast<uint32_t*>(s.pwin)[i] = 0xFFFFFFFFu;
             for (int i = tid; i < L.P_pad / 32 + 1; i += nt) s.isx[i] = 0;
@@ -1152,7 +1146,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 const int n = s.sc[SC_NLIST];
                 const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
                 const int l4 = lane & 3;
-                uint32_t* cg32 = reinterpret_cast<uint32_t*>(s.cgrid + (tk & 1) * HASH_BINS);
                 for (int qb = (tid >> 5) * 8; qb < n; qb += nt >> 2) {  // 8 cells per warp pass, warp-uniform
                     const int q = qb + (lane >> 2);
                     const int g = q < n ? s.list[q] : s.list[0];
@@ -1176,11 +1169,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     if (l4 == 0) {
                         cx[g] = x; cy[g] = y; cix[g] = ix; ciy[g] = iy;
                         if (t > 0.0f) ct[g] = t - 1.0f;
-                        // register the cell in this tick's cell-count grid (one byte per hash bin; a carry out of a
-                        // byte only makes a neighbour look occupied, which is the safe side)
-                        const int b = hash_coord(p, y) * HASH_W + hash_coord(p, x);
-                        atomicAdd(cg32 + (b >> 2), 1u << ((b & 3) * 8));
-                        if (!(r2 < bs2)) s.sc[SC_BIGCELL] = 1;
                     }
                     const float rp = r * 1.001f + 0.01f;
                     const int bx0 = hash_coord(p, x - rp), bx1 = hash_coord(p, x + rp);
@@ -1210,8 +1198,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             }
             __syncthreads();
             PHASE(6);  // motion + query (+ barrier)
-            // the other parity's cell-count grid was last read in the previous tick: clear it for the next one
-            if (tid < HASH_BINS / 4) reinterpret_cast<uint32_t*>(s.cgrid + ((tk + 1) & 1) * HASH_BINS)[tid] = 0u;
             const int nh = s.sc[SC_NHITS];                // block-uniform from here on
             const bool food_any = s.sc[SC_FOODANY] != 0;
             const bool gains = nh > 0 || food_any;        // some mass changes this tick before the eat test
@@ -1245,11 +1231,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 for (int q = tid; q < n; q += nt) {
                     const int g = s.list[q];
                     const int e = cnt_get(s.cnt32, g);
-                    if (e) {
-                        const float m = cm[g] + (float)e * c.pellet_mass;
-                        cm[g] = m; cnt_clear(s.cnt32, g);
-                        if (!(m * r2pm < bs2)) s.sc[SC_BIGCELL] = 1;
-                    }
+                    if (e) { cm[g] = cm[g] + (float)e * c.pellet_mass; cnt_clear(s.cnt32, g); }
                 }
                 __syncthreads();
                 for (int f = tid; f < F; f += nt) {
@@ -1278,15 +1260,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             PHASE(7);  // resolve, foods
             // cell-eats-cell test (different players, pre-phase snapshot): four lanes per prey, each
             // scanning a quarter of the possible eaters; the lowest gid wins
-            // Cull: an eater holds the prey's centre, so it is closer than its own radius; while every radius is
-            // below the hash bin size (SC_BIGCELL == 0) it sits in one of the 3x3 bins around the prey.  The
-            // motion phase counted the alive cells per bin, so a prey whose neighbourhood holds no other cell
-            // skips the scan (cells made by a virus pop after the count share their parent's player and bin).
+            // Measured and dropped (profiles/r01i_notes.txt): culling the scan through per-bin cell counts or bin
+            // heads shortens a lone CTA's critical path but not the throughput at 7 CTAs per SM.
             auto eat_test = [&]() {
                 const int n = s.sc[SC_NLIST];
                 const int l4 = lane & 3;
-                const bool cull = s.sc[SC_BIGCELL] == 0;  // block-uniform
-                const uint8_t* cg = s.cgrid + (tk & 1) * HASH_BINS;
                 for (int qb = (tid >> 5) * 8; qb < n; qb += nt >> 2) {  // 8 preys per warp pass, warp-uniform
                     const int q = qb + (lane >> 2);
                     const int j = q < n ? s.list[q] : s.list[0];
@@ -1294,20 +1272,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     const float need = mj * c.eat_ratio, x = cx[j], y = cy[j];
                     const int kj = j >> 4;
                     int best = NONE_I;
-                    bool cand = mj > 0.0f;
-                    if (cull) {
-                        int tot = 0;
-                        const int bx = hash_coord(p, x), row = hash_coord(p, y) - 1 + l4;
-                        if (cand && l4 < 3 && row >= 0 && row < HASH_W) {
-                            const uint8_t* rp = cg + row * HASH_W;
-                            tot = (int)rp[bx] + (bx > 0 ? (int)rp[bx - 1] : 0) + (bx < HASH_W - 1 ? (int)rp[bx + 1] : 0);
-                        }
-                        tot += __shfl_xor_sync(FULL, tot, 1);
-                        tot += __shfl_xor_sync(FULL, tot, 2);
-                        cand = tot > 1;  // the prey itself is counted
-                    }
-                    if (!__any_sync(FULL, cand)) continue;  // warp-uniform
-                    if (cand) {
+                    if (mj > 0.0f) {
 #pragma unroll 4
                         for (int qi = l4; qi < n; qi += 4) {
                             const int i = s.list[qi];
@@ -1331,10 +1296,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     const int g = s.list[q];
                     float m = cm[g];
                     const int e = cnt_get(s.cnt32, g);
-                    if (e) {
-                        m = m + (float)e * unit; cm[g] = m; cnt_clear(s.cnt32, g);
-                        if (!(m * r2pm < bs2)) s.sc[SC_BIGCELL] = 1;
-                    }
+                    if (e) { m = m + (float)e * unit; cm[g] = m; cnt_clear(s.cnt32, g); }
                     if (V > 0 && m >= c.virus_pop_mass) {
                         const float r2 = m * r2pm, x = cx[g], y = cy[g];
                         for (int v = 0; v < V; ++v) {
