@@ -1018,9 +1018,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     for (int row = y0; row <= y1; ++row) {
                         const int j1 = s.hstart[row * HASH_W + x1 + 1];
                         for (int j = s.hstart[row * HASH_W + x0] + l4; j < j1; j += 4) {
-                            const int i = s.sorted[j];
-                            if ((s.isx[i >> 5] >> (i & 31)) & 1) continue;  // stale entry
-                            const float qx = px[i];
+                            const int i = s.sorted[j];  // an entry of a pellet that respawned since the build is harmless:
+                            const float qx = px[i];     // it is judged at its true position (and again from the respawn list)
                             if (!(qx >= 0.0f)) continue;
                             float dx = qx - Cx, dy = py[i] - Cy;
                             if (fabsf(dx) <= R && fabsf(dy) <= R) {
