@@ -56,6 +56,18 @@ def algorithmic_bytes_per_env_step(w=None):
     return 8 * P + 12 * V + 2 * 24 * K * 16 + 2 * 16 * F + A * (12 + 5) + 32 + A * C * G * G * 4
 
 
+def ncu_traffic_bytes(world, arenas):
+    """DRAM bytes of one step-kernel launch from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)[world]
+        if int(t["arenas"]) != int(arenas):
+            return None
+        return int(t["dram_read_bytes"]) + int(t["dram_write_bytes"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -246,7 +258,7 @@ def run_cuda(args):
                     "steps": Ke, "api": "agar_step_host (pinned host buffers; obs D2H every step)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "agar_step_kernel", "bytes_per_env_step": B,
+                         "traffic": ncu_traffic_bytes(args.world, N) if not args.set else None, "kernel": "agar_step_kernel", "bytes_per_env_step": B,
                          "env_steps_per_launch": N, "launch_us": launch_s * 1e6, "peak_source": peak_src},
         }
         if world == 1 and not args.no_cpu_baseline:
