@@ -166,7 +166,12 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
     }
     const bool generic_only = std::getenv("AGAR_GENERIC_KERNEL") != nullptr;  // tuning/test switch: never specialise
     if (!generic_only && matches<CvCfg2>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 7, CvCfg2>; e->kernel_name = "cfg2"; }
-    else if (!generic_only && matches<CvCfg1>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 8, CvCfg1>; e->kernel_name = "cfg1"; }
+    else if (!generic_only && matches<CvCfg1>(*cfg, p.L)) {
+        e->kernel_name = "cfg1";
+        const char* mb = std::getenv("AGAR_MIN_BLOCKS");
+        const int v = mb ? std::atoi(mb) : 10;  // measured on B200: 8 CTAs/SM 59.3 M, 10 (<=51 regs) 65.1 M, 12 (40 regs) 64.2 M env-steps/s
+        e->kernel = v == 8 ? agar_step_kernel<kThreads, 8, CvCfg1> : (v == 12 ? agar_step_kernel<kThreads, 12, CvCfg1> : agar_step_kernel<kThreads, 10, CvCfg1>);
+    }
     else if (!generic_only && matches<CvCfg4>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 8, CvCfg4>; e->kernel_name = "cfg4"; }
     else {
         e->kernel_name = "generic";
