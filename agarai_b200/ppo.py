@@ -85,6 +85,8 @@ class PPOConfig:
     lr_scale: tuple = (1.0, 1.0, 10.0)
     grad_clip: float = 1.0           # optimizers.clip_grads(dparams, 1), ppo/train.py:331
     keep_observations: bool = False  # True: keep [T,B,C,G,G] observations instead of state snapshots
+    amp_bf16: bool = False           # policy network under torch.autocast(bfloat16) + channels_last (the policy is
+                                     # plain PyTorch and outside the parity scope; the env path stays float32)
 
 
 class PPOTrainer:
@@ -95,6 +97,8 @@ class PPOTrainer:
         self.dev = env.device
         torch.manual_seed(seed)
         self.model = ActorCritic(env.observation_space.shape, env.num_actions, cfg.num_features).to(self.dev)
+        if cfg.amp_bf16:
+            self.model = self.model.to(memory_format=torch.channels_last)
         self.net = nn.parallel.DistributedDataParallel(self.model, device_ids=[self.dev.index]) if ddp else self.model
         groups = [list(self.model.features.parameters()) + list(self.model.dense.parameters()),
                   list(self.model.actor.parameters()), list(self.model.critic.parameters())]
@@ -111,6 +115,14 @@ class PPOTrainer:
     def _flat(self, obs):
         return obs.reshape((self.B,) + tuple(obs.shape[2:]))
 
+    def _policy(self, obs):
+        """logits, values in float32 (optionally evaluated under bf16 autocast)"""
+        if not self.cfg.amp_bf16:
+            return self.net(obs)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits, values = self.net(obs.contiguous(memory_format=torch.channels_last))
+        return logits.float(), values.float()
+
     @torch.no_grad()
     def collect(self):
         """get_rollouts (ppo/train.py:156-197) for all arenas at once."""
@@ -118,7 +130,7 @@ class PPOTrainer:
         self.roll.clear()
         self.model.train()  # the reference always builds the extractor with mode='train' (App. D)
         for t in range(T):
-            logits, values = self.net(self._flat(self.obs))
+            logits, values = self._policy(self._flat(self.obs))
             actions = torch.multinomial(F.softmax(logits, 1), 1, generator=self.gen)[:, 0]
             rec = {"actions": actions, "values": values, "action_logits": logits}
             rec["observations" if self.cfg.keep_observations else "state"] = (
@@ -127,7 +139,7 @@ class PPOTrainer:
             rec["rewards"] = reward.reshape(self.B)
             rec["dones"] = done.reshape(self.B)
             self.roll.record(rec)
-        _, boot = self.net(self._flat(self.obs))
+        _, boot = self._policy(self._flat(self.obs))
         self.roll.record({"values": boot})  # bootstrap row, ppo/train.py:189-195
 
     def advantages(self):
@@ -151,7 +163,7 @@ class PPOTrainer:
         for _ in range(cfg.num_sgd_steps):
             pick = torch.randperm(T * self.B, generator=self.gen, device=self.dev)[:cfg.batch_size]
             t_idx, b_idx = pick // self.B, pick % self.B
-            logits, values = self.net(self._observations(t_idx, b_idx))
+            logits, values = self._policy(self._observations(t_idx, b_idx))
             la = ppo_actor_loss(logits, self.roll["actions"][t_idx, b_idx], adv[t_idx, b_idx],
                                 self.roll["action_logits"][t_idx, b_idx], cfg.clip_eps)
             lc = critic_loss(values, ret[t_idx, b_idx])
