@@ -366,11 +366,11 @@ int agar_gae(const float* d_reward, const float* d_value, const uint8_t* d_done,
     if (!d_adv && !d_ret) return fail("agar_gae: nothing to compute");
     const float g = (float)gamma, cgl = (float)(gamma * lam);
     // tuning switches (defaults are the measured best on B200, profiles/): steps per register batch and block size.
-    // A 4-columns-per-thread variant with 128-bit loads was measured slower (too few threads: 60 us vs 38 us).
+    // Variants with 2 or 4 columns per thread (64/128-bit loads) were measured slower: too few threads (55 / 60 us vs 38 us).
     static const int tune_u = std::getenv("AGAR_GAE_U") ? std::atoi(std::getenv("AGAR_GAE_U")) : 16;
-    static const int tune_b = std::getenv("AGAR_GAE_BLOCK") ? std::atoi(std::getenv("AGAR_GAE_BLOCK")) : 64;
+    static const int tune_b = std::getenv("AGAR_GAE_BLOCK") ? std::atoi(std::getenv("AGAR_GAE_BLOCK")) : 32;
     cudaStream_t st = (cudaStream_t)stream;
-    const int threads = (tune_b == 32 || tune_b == 128 || tune_b == 256) ? tune_b : 64, blocks = (N + threads - 1) / threads;
+    const int threads = (tune_b == 64 || tune_b == 128) ? tune_b : 32, blocks = (N + threads - 1) / threads;
     if (tune_u == 8) agar_gae_kernel<8><<<blocks, threads, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N);
     else agar_gae_kernel<16><<<blocks, threads, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N);
     CUDA_OK(cudaGetLastError());
