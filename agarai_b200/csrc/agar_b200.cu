@@ -69,7 +69,8 @@ struct AgarEnv {
     // staging for agar_step_host
     float* d_target = nullptr; int32_t* d_act = nullptr; float* d_obs = nullptr;
     float* d_reward = nullptr; uint8_t* d_done = nullptr;
-    cudaStream_t host_stream = nullptr;
+    cudaStream_t host_stream = nullptr, host_stream2 = nullptr;
+    cudaEvent_t host_event = nullptr;
 };
 
 namespace {
@@ -206,6 +207,8 @@ int agar_destroy(AgarEnv* e) {
     cudaFree(e->d_tab_xy); cudaFree(e->d_tab_act);
     cudaFree(e->d_target); cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_reward); cudaFree(e->d_done);
     if (e->host_stream) cudaStreamDestroy(e->host_stream);
+    if (e->host_stream2) cudaStreamDestroy(e->host_stream2);
+    if (e->host_event) cudaEventDestroy(e->host_event);
     delete e;
     return 0;
 }
@@ -337,23 +340,43 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
     if (!e) return fail("env is NULL");
     if (!h_target_xy || !h_act || !h_reward || !h_done) return fail("agar_step_host: NULL buffer");
     CUDA_OK(cudaSetDevice(e->device));
-    const size_t NA = (size_t)e->p.c.num_arenas * e->p.c.num_agents;
+    const size_t N = (size_t)e->p.c.num_arenas, A = (size_t)e->p.c.num_agents, NA = N * A;
     if (!e->host_stream) {
         CUDA_OK(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&e->host_stream2, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&e->host_event, cudaEventDisableTiming));
         CUDA_OK(cudaMalloc(&e->d_target, NA * 2 * sizeof(float)));
         CUDA_OK(cudaMalloc(&e->d_act, NA * sizeof(int32_t)));
         CUDA_OK(cudaMalloc(&e->d_reward, NA * sizeof(float)));
         CUDA_OK(cudaMalloc(&e->d_done, NA));
     }
     if (h_obs && !e->d_obs) CUDA_OK(cudaMalloc(&e->d_obs, obs_elems(e) * sizeof(float)));
-    cudaStream_t st = e->host_stream;
+    cudaStream_t st = e->host_stream, st2 = e->host_stream2;
     CUDA_OK(cudaMemcpyAsync(e->d_target, h_target_xy, NA * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(e->d_act, h_act, NA * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (int rc = agar_step(e, e->d_target, e->d_act, h_obs ? e->d_obs : nullptr, e->d_reward, e->d_done, st)) return rc;
-    if (h_obs) CUDA_OK(cudaMemcpyAsync(h_obs, e->d_obs, obs_elems(e) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // The observation copy (48 KB per agent) dominates: the batch is stepped in chunks so that the device-to-host
+    // copy of one chunk (copy stream) overlaps the kernel of the next (compute stream).
+    const size_t per_arena = A * (size_t)e->p.C * e->p.c.grid_size * e->p.c.grid_size;
+    const int chunks = (h_obs && N >= 1024) ? 4 : 1;
+    for (int k = 0; k < chunks; ++k) {
+        const int a0 = (int)(N * k / chunks), a1 = (int)(N * (k + 1) / chunks);
+        KArgs a = base_args(e);
+        a.flags = F_STEP | (h_obs ? F_OBS : 0);
+        a.target_xy = e->d_target; a.act = e->d_act; a.obs = h_obs ? e->d_obs : nullptr;
+        a.reward = e->d_reward; a.done = e->d_done;
+        a.arena0 = a0;
+        if (int rc = launch(e, a, a1 - a0, st)) return rc;
+        if (h_obs) {
+            CUDA_OK(cudaEventRecord(e->host_event, st));
+            CUDA_OK(cudaStreamWaitEvent(st2, e->host_event, 0));
+            CUDA_OK(cudaMemcpyAsync(h_obs + a0 * per_arena, e->d_obs + a0 * per_arena, (size_t)(a1 - a0) * per_arena * sizeof(float),
+                                    cudaMemcpyDeviceToHost, st2));
+        }
+    }
     CUDA_OK(cudaMemcpyAsync(h_reward, e->d_reward, NA * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaMemcpyAsync(h_done, e->d_done, NA, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaStreamSynchronize(st2));
     return 0;
 }
 

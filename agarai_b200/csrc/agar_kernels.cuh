@@ -71,6 +71,7 @@ struct KArgs {
     int32_t* hash;           // [N, hash_words] persisted pellet hash (null: rebuild every step)
     int32_t flags;
     int32_t n_records;
+    int32_t arena0;          // first arena of this launch (agar_step_host steps the batch in chunks)
 };
 
 enum { F_STEP = 1, F_RESET = 2, F_OBS = 4, F_READONLY = 8 };
@@ -872,7 +873,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     const Smem s = carve(smem_raw, L, G);
     const int tid = threadIdx.x, nt = kThreads, lane = tid & 31;
     const int hbase = lane & 16, slot = lane & 15;
-    const int arena = blockIdx.x;
+    const int arena = a.arena0 + blockIdx.x;
     const int A = CV_INT(A, c.num_agents), K = CV_INT(K, p.K), KC = CV_INT(KC, p.KC), V = CV_INT(V, c.num_viruses), F = CV_INT(F, c.max_foods);
     const uint64_t gid64 = (uint64_t)(c.arena_id_base + arena);
     const uint32_t gid_lo = (uint32_t)gid64, gid_hi = (uint32_t)(gid64 >> 32);

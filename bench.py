@@ -255,7 +255,7 @@ def run_cuda(args):
                        **WORLD},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "api": "agar_step_host (pinned host buffers; obs D2H every step)"},
+                    "steps": Ke, "api": "agar_step_host (pinned host buffers; obs D2H every step, 4 chunks: copy of one overlaps the kernel of the next)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_bytes(args.world, N) if not args.set else None, "kernel": "agar_step_kernel", "bytes_per_env_step": B,
