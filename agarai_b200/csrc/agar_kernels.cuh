@@ -479,7 +479,7 @@ __device__ __noinline__ void build_hash(const DevParams& p) {
 }
 
 // all threads: unordered list of the alive cells' gids, per-player alive masks, "some player has
-// several cells" flag.  SC_NLIST and SC_MULTI must be 0 on entry (a barrier earlier).
+// several cells" flag, list-membership bits.  SC_NLIST and SC_MULTI must be 0 on entry (a barrier earlier).
 template <class CV>
 __device__ __forceinline__ void build_list(const DevParams& p, const Smem& s) {
     decltype(auto) L = layout_of<CV>(p);
@@ -489,6 +489,7 @@ __device__ __forceinline__ void build_list(const DevParams& p, const Smem& s) {
         const int g = base + tid;
         const bool al = g < KC && s.rec[L.cell_m + g] > 0.0f;
         const unsigned b = __ballot_sync(0xffffffffu, al);
+        if (lane == 0 && g < KC) s.sc[32 + (g >> 5)] = (int)b;  // membership bits of the list (sc[32..63])
         if (g < KC && (lane & 15) == 0) {
             unsigned hm = (b >> (lane & 16)) & 0xFFFFu;
             s.pmask[g >> 4] = (int)hm;
@@ -931,11 +932,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             build_hash<CV>(p);
         }
         build_list<CV>(p, s);
-        for (int base = 0; base < KC; base += nt) {  // membership bits of the list (one word per warp chunk)
-            const int g = base + tid;
-            const unsigned b = __ballot_sync(0xffffffffu, g < KC && cm[g] > 0.0f);
-            if (lane == 0 && g < KC) inl[g >> 5] = (int)b;
-        }
         __syncthreads();
         PHASE(1);  // hash check/build, list
         // ---- players: bot respawn, centroid and mass of single-cell players (thread per player) ----
