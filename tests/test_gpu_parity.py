@@ -556,3 +556,23 @@ def test_compile_time_specialised_kernels_match_oracle_and_generic_kernel(oracle
         assert torch.equal(g_o, r_o) and torch.equal(g_r, r_r) and torch.equal(g_d, r_d)
         assert torch.equal(genv.get_state(), renv.get_state())
     genv.close(); renv.close()
+
+
+def test_step_host_chunked_path_equals_device_step(oracle):
+    """agar_step_host steps batches of >= 1024 arenas in four chunks (observation copy of one chunk overlapping
+    the kernel of the next): host results equal the device-buffer step of a twin env, ragged chunk sizes."""
+    import agarai_b200 as ab
+    kw = dict(num_arenas=1501, num_agents=2, num_bots=2, num_viruses=3, num_pellets=150, arena_size=90.0, grid_size=16,
+              obs_flags=15, auto_reset=1)
+    e1 = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=7)
+    e2 = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=7)
+    e1.reset(); e2.reset()
+    rng = np.random.default_rng(1)
+    obs = np.empty(e1.obs_shape, np.float32); rew = np.empty((1501, 2), np.float32); done = np.empty((1501, 2), np.uint8)
+    for t in range(6):
+        xy, act = random_actions(rng, 1501, 2, (0, 1, 2), 0.5)
+        e1.step_host(xy, act, obs, rew, done)
+        o, r, d, _ = e2.step(torch.from_numpy(xy).cuda(), torch.from_numpy(act).cuda())
+        assert np.array_equal(obs, o.cpu().numpy()) and np.array_equal(rew, r.cpu().numpy()) and np.array_equal(done, d.cpu().numpy())
+    assert torch.equal(e1.get_state(), e2.get_state())
+    e1.close(); e2.close()
