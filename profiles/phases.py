@@ -37,7 +37,7 @@ MARKS = [
     ("raster: mass patches (warp 0)", "// ---- warp 0: own cells and others"),
     ("raster: count channels", "// ---- count channels ----"),
     ("virus pops (out of line)", "__device__ __noinline__ void virus_pops"),
-    ("kernel: prelude + stage record", "template <int kThreads, int kMinBlocks>"),
+    ("kernel: prelude + stage record", "template <int kThreads, int kMinBlocks, class CV>"),
     ("step start: hash check, list", "// ---- pellet hash (persisted across steps"),
     ("step start: players", "// ---- players: bot respawn, centroid"),
     ("step start: multi-cell players", "// ---- players with several cells"),
@@ -45,7 +45,7 @@ MARKS = [
     ("step start: bots", "// ---- bots: nearest pellet in the square"),
     ("step start: split", "// ---- split: i-th eligible"),
     ("step start: feed", "// ---- feed: cells in gid order"),
-    ("tick: motion + pellet query", "for (int tk = 0; tk < c.ticks_per_step"),
+    ("tick: motion + pellet query", "for (int tk = 0; tk < TICKS; ++tk)"),
     ("tick: resolve pellets, foods", "// ---- resolve the claimed pellets"),
     ("tick: eat test lambda + apply gains", "// cell-eats-cell test (different players"),
     ("tick: eat loop, eat apply", "// ---- cell eats cell (one code site)"),
