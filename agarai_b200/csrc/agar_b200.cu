@@ -394,8 +394,16 @@ int agar_gae(const float* d_reward, const float* d_value, const uint8_t* d_done,
     static const int tune_b = std::getenv("AGAR_GAE_BLOCK") ? std::atoi(std::getenv("AGAR_GAE_BLOCK")) : 32;
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = (tune_b == 64 || tune_b == 128) ? tune_b : 32, blocks = (N + threads - 1) / threads;
-    if (tune_u == 8) agar_gae_kernel<8><<<blocks, threads, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N);
-    else agar_gae_kernel<16><<<blocks, threads, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N);
+    static const int tune_nb = std::getenv("AGAR_GAE_NB") ? std::atoi(std::getenv("AGAR_GAE_NB")) : 2;
+#define GAE_LAUNCH(U_, NB_) agar_gae_kernel<U_, NB_><<<blocks, threads, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N)
+    if (tune_u == 8 && tune_nb == 2) GAE_LAUNCH(8, 2);
+    else if (tune_u == 8 && tune_nb == 3) GAE_LAUNCH(8, 3);
+    else if (tune_u == 8 && tune_nb == 4) GAE_LAUNCH(8, 4);
+    else if (tune_u == 8 && tune_nb == 6) GAE_LAUNCH(8, 6);
+    else if (tune_u == 16 && tune_nb == 3) GAE_LAUNCH(16, 3);
+    else if (tune_u == 16 && tune_nb == 4) GAE_LAUNCH(16, 4);
+    else GAE_LAUNCH(16, 2);
+#undef GAE_LAUNCH
     CUDA_OK(cudaGetLastError());
     return 0;
 }

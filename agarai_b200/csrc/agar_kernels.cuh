@@ -1471,7 +1471,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
 // time-major [T,N] rollout buffer: one thread per column, reverse scan over t.  The recurrence is
 // sequential in t (and must stay so: the float sequence is the reference's), so the kernel is a
 // memory-latency problem: the loads of the NEXT batch of U steps are issued before the dependent
-// chain of the current batch runs (two register buffers), which keeps 2U rows in flight per thread.
+// chain of the current batch runs (a ring of NB register batches keeps (NB-1)*U rows in flight per thread).
 template <int U>
 struct GaeBatch { float r[U], v[U]; uint8_t d[U]; };
 
@@ -1516,7 +1516,7 @@ __device__ __forceinline__ void gae_scan(const GaeBatch<U>& b, float g, float cg
     }
 }
 
-template <int U>
+template <int U, int NB>
 __global__ void __launch_bounds__(256) agar_gae_kernel(const float* __restrict__ r, const float* __restrict__ v,
                                                       const uint8_t* __restrict__ done,
                                                       const float* __restrict__ end_value, float g, float cgl,
@@ -1524,17 +1524,23 @@ __global__ void __launch_bounds__(256) agar_gae_kernel(const float* __restrict__
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const bool want_v = adv != nullptr;
-    GaeBatch<U> b0, b1;
-    gae_load<U>(b0, r, v, done, want_v, T, N, n);
+    // ring of NB register batches: NB-1 batches of loads are in flight while one batch is scanned
+    GaeBatch<U> b[NB];
+#pragma unroll
+    for (int k = 0; k < NB - 1; ++k)
+        if (T - k * U > 0) gae_load<U>(b[k], r, v, done, want_v, T - k * U, N, n);
     float a_next = 0.0f;
     float g_next = end_value ? end_value[n] : 0.0f;
     float v_next = want_v ? __ldcs(v + (size_t)T * N + n) : 0.0f;
-    for (int t1 = T; t1 > 0; t1 -= 2 * U) {
-        if (t1 - U > 0) gae_load<U>(b1, r, v, done, want_v, t1 - U, N, n);
-        gae_scan<U>(b0, g, cgl, adv, ret, t1, T, N, n, a_next, g_next, v_next);
-        if (t1 - U <= 0) break;
-        if (t1 - 2 * U > 0) gae_load<U>(b0, r, v, done, want_v, t1 - 2 * U, N, n);
-        gae_scan<U>(b1, g, cgl, adv, ret, t1 - U, T, N, n, a_next, g_next, v_next);
+    for (int t1 = T; t1 > 0; t1 -= NB * U) {
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            const int tcur = t1 - k * U;
+            if (tcur <= 0) break;
+            const int tpre = tcur - (NB - 1) * U;
+            if (tpre > 0) gae_load<U>(b[(k + NB - 1) % NB], r, v, done, want_v, tpre, N, n);
+            gae_scan<U>(b[k], g, cgl, adv, ret, tcur, T, N, n, a_next, g_next, v_next);
+        }
     }
 }
 
