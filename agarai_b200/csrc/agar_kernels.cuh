@@ -736,7 +736,9 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                     // respawned since the hash was built; those come from the respawn list instead
                     const int bx0 = hash_coord(p, cx - lim), bx1 = hash_coord(p, cx + lim);
                     const int by0 = hash_coord(p, cy - lim), by1 = hash_coord(p, cy + lim);
-                    for (int by = by0 + (tid >> 5); by <= by1; by += nt >> 5) {
+                    // warp 0 is busy with the mass patches above: the other warps share the hash rows
+                    const int nw = (nt >> 5) > 1 ? (nt >> 5) - 1 : 1, wi = (nt >> 5) > 1 ? (tid >> 5) - 1 : 0;
+                    for (int by = by0 + wi; wi >= 0 && by <= by1; by += nw) {
                         const int j1 = s.hstart[by * HASH_W + bx1 + 1];
                         for (int j = s.hstart[by * HASH_W + bx0] + lane; j < j1; j += 32) {
                             const int i = s.sorted[j];
