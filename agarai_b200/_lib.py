@@ -65,6 +65,7 @@ SYMBOLS = [
     ("agar_observe_ram", C.c_int, [_P] + [C.c_int32] * 5 + [_P, _P]),
     ("agar_screen_gray", C.c_int, [_P, C.c_int64, _P, C.c_int32, _P]),
     ("agar_launch_count", C.c_int64, [_P]),
+    ("agar_kernel_variant", C.c_char_p, [_P]),
 ]
 
 _lib = None

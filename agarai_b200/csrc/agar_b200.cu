@@ -39,6 +39,10 @@ using StepKernel = void (*)(DevParams, KArgs);
 using CvCfg1 = StCfg<1, 0, 1000, 0, 64, 64, 7, 4>;    // configs[0]/[2]/[4]: single agent, pellets only
 using CvCfg2 = StCfg<1, 25, 1000, 25, 64, 64, 7, 4>;  // configs[1]: 25 bots + 25 viruses
 using CvCfg4 = StCfg<16, 0, 1000, 0, 64, 64, 7, 4>;   // configs[3]: 16 agents per arena
+// the reference's own default worlds
+using CvA2C = StCfg<32, 0, 1000, 25, 64, 32, 15, 4>;     // a2c/hyperparameters.py:89-107: 32 agents, 25 viruses, grid 32
+using CvA2CTest = StCfg<8, 25, 1000, 25, 64, 32, 15, 4>; // a2c/train.py:17-34: 8 agents + 25 bots
+using CvDQN = StCfg<1, 0, 30, 0, 64, 128, 15, 4>;        // dqn/hyperparameters.py:23-28,97-104: arena 45, 30 pellets, grid 128
 
 template <class CV>
 bool matches(const AgarConfig& c, const AgarLayout& L) {
@@ -174,6 +178,9 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
         e->kernel = v == 8 ? agar_step_kernel<kThreads, 8, CvCfg1> : (v == 12 ? agar_step_kernel<kThreads, 12, CvCfg1> : agar_step_kernel<kThreads, 10, CvCfg1>);
     }
     else if (!generic_only && matches<CvCfg4>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 8, CvCfg4>; e->kernel_name = "cfg4"; }
+    else if (!generic_only && matches<CvA2C>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 6, CvA2C>; e->kernel_name = "a2c"; }
+    else if (!generic_only && matches<CvA2CTest>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 6, CvA2CTest>; e->kernel_name = "a2c_test"; }
+    else if (!generic_only && matches<CvDQN>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 8, CvDQN>; e->kernel_name = "dqn"; }
     else {
         e->kernel_name = "generic";
         switch (e->min_blocks) {
@@ -450,6 +457,7 @@ int agar_screen_gray(const uint8_t* d_rgb, int64_t n_pixels, void* d_out, int32_
 }
 
 int64_t agar_launch_count(const AgarEnv* e) { return e ? e->launches : 0; }
+const char* agar_kernel_variant(const AgarEnv* e) { return e ? e->kernel_name : ""; }
 
 #ifdef AGAR_PHASE_CLOCKS
 // tuning builds only (not declared in the header): cycles charged to each phase id since the last call

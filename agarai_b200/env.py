@@ -277,6 +277,11 @@ class BatchedAgarioEnv:
     def launch_count(self) -> int:
         return int(self._L.agar_launch_count(self._h))
 
+    @property
+    def kernel_variant(self) -> str:
+        """"generic" or the name of the compile-time specialised step kernel this env runs"""
+        return self._L.agar_kernel_variant(self._h).decode()
+
 
 class GymCompatEnv:
     """One arena of a BatchedAgarioEnv with the reference's calling convention.

@@ -40,6 +40,13 @@ WORLDS = {
     # configs[3] world: 16 agents per arena with split/merge (ppo.textproto:4-23)
     "cfg4": dict(num_agents=16, num_bots=0, num_viruses=0, num_pellets=1000, arena_size=1000.0, ticks_per_step=4,
                  grid_size=64, obs_flags=7, pellet_regen=1, auto_reset=1, max_foods=64),
+    # the reference's own default worlds (a2c/hyperparameters.py:89-107, a2c/train.py:17-34, dqn/hyperparameters.py:23-28)
+    "a2c": dict(num_agents=32, num_bots=0, num_viruses=25, num_pellets=1000, arena_size=500.0, ticks_per_step=4,
+                grid_size=32, obs_flags=15, pellet_regen=1, auto_reset=1, max_foods=64),
+    "a2c_test": dict(num_agents=8, num_bots=25, num_viruses=25, num_pellets=1000, arena_size=500.0, ticks_per_step=4,
+                     grid_size=32, obs_flags=15, pellet_regen=1, auto_reset=1, max_foods=64),
+    "dqn": dict(num_agents=1, num_bots=0, num_viruses=0, num_pellets=30, arena_size=45.0, ticks_per_step=4,
+                grid_size=128, obs_flags=15, pellet_regen=1, auto_reset=1, max_foods=64, view_size=30.0),
 }
 WORLD = WORLDS["cfg2"]
 METRIC = "env_steps_per_sec_incl_grid_obs"
@@ -153,7 +160,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.world}: {WORLD['num_agents']} agent(s) + {WORLD['num_bots']} bots + "
                                f"{WORLD['num_viruses']} viruses, {WORLD['num_pellets']} pellets, arena "
-                               f"{WORLD['arena_size']:g}, obs 3x64x64 f32 per agent",
+                               f"{WORLD['arena_size']:g}, obs {bin(WORLD['obs_flags']).count('1')}x{WORLD['grid_size']}x{WORLD['grid_size']} f32 per agent",
                    "arenas_per_step": sample, **WORLD},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} arenas x {args.steps} steps (of the {ARENAS_PER_GPU}-arena workload), "
@@ -247,7 +254,7 @@ def run_cuda(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.world}: {N} arenas/GPU, {A} agent(s) + {WORLD['num_bots']} bots + "
                                    f"{WORLD['num_viruses']} viruses, {WORLD['num_pellets']} pellets, arena "
-                                   f"{WORLD['arena_size']:g}, obs 3x64x64 f32 per agent, random policy over 25 actions "
+                                   f"{WORLD['arena_size']:g}, obs {bin(WORLD['obs_flags']).count('1')}x{WORLD['grid_size']}x{WORLD['grid_size']} f32 per agent, random policy over 25 actions "
                                    "(8 dirs, split, feed)",
                        "arenas_per_gpu": N,
                        "l2": f"no flush: each step streams {env.layout.words * 4 * N / 1e6:.0f} MB of state and writes "

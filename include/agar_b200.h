@@ -266,6 +266,9 @@ int agar_screen_gray(const uint8_t* d_rgb, int64_t n_pixels, void* d_out, int32_
 
 /* number of kernel launches issued by this handle since creation (bench bookkeeping) */
 int64_t agar_launch_count(const AgarEnv* env);
+/* which instantiation of the step kernel the handle launches: "generic" (sizes read at run time) or the name of a
+ * compile-time specialised world ("cfg1", "cfg2", "cfg4", "a2c", "a2c_test", "dqn") */
+const char* agar_kernel_variant(const AgarEnv* env);
 
 #ifdef __cplusplus
 }

@@ -526,7 +526,7 @@ def test_ram_env_id_and_full_observation_view(oracle):
     benv.close()
 
 
-@pytest.mark.parametrize("world", ["cfg1", "cfg2", "cfg4"])
+@pytest.mark.parametrize("world", ["cfg1", "cfg2", "cfg4", "a2c", "a2c_test", "dqn"])
 def test_compile_time_specialised_kernels_match_oracle_and_generic_kernel(oracle, world):
     """The BASELINE worlds run step kernels whose sizes and record offsets are compile-time constants
     (agar_kernels.cuh "config views").  Same source as the generic kernel: states, observations, rewards and
@@ -540,6 +540,7 @@ def test_compile_time_specialised_kernels_match_oracle_and_generic_kernel(oracle
         renv = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=31)  # same world on the runtime-config kernel
     finally:
         del os.environ["AGAR_GENERIC_KERNEL"]
+    assert genv.kernel_variant == world and renv.kernel_variant == "generic"
     rng = np.random.default_rng(8)
     N, A = 24, kw["num_agents"]
     g0 = genv.reset(); r0 = renv.reset()
