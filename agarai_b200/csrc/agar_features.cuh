@@ -80,30 +80,75 @@ __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* key, int n)
 // :197-204): the n entities nearest to loc by float32 sqrt(dx*dx + dy*dy), ties by index (the stable order;
 // numpy's default argsort leaves ties unspecified), as positions relative to loc; zero rows pad.
 // key = distance bits (non-negative floats order like their bit patterns) << 32 | index.
-__device__ void ram_nearest_points(unsigned long long* key, int cap, const float* ex, const float* ey, int count,
-                                   bool marker, float lx, float ly, int n, float* __restrict__ out) {
-    const int tid = threadIdx.x, nt = blockDim.x;
+// With many more entities than wanted, only the entities inside a radius that certainly holds n of them are
+// sorted: four candidate radii (multiples of the radius a uniform density would need) are counted in one pass,
+// the smallest sufficient one selects the candidates, which are compacted and sorted; the n nearest of all are
+// among them, so the result is the full sort's.  Otherwise (few entities, or no radius qualifies) everything is
+// sorted.
+#define RAM_CAND_CAP 512
+__device__ void ram_nearest_points(unsigned long long* key, unsigned long long* cand, int* scal, int cap, const float* ex,
+                                   const float* ey, int count, bool marker, float lx, float ly, int n, float arena,
+                                   float* __restrict__ out) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     int m = 1;
     while (m < count) m <<= 1;
     if (m > cap) m = cap;
-    for (int i = tid; i < m; i += nt) {
+    const bool preselect = m > 256 && n * 4 < count;  // block-uniform
+    float rad[4];
+    if (preselect) {
+        const float r0 = sqrtf((float)n * arena * arena / (3.14159265f * (float)count));
+        rad[0] = r0 * 1.5f; rad[1] = r0 * 2.5f; rad[2] = r0 * 4.0f; rad[3] = r0 * 7.0f;
+        if (tid < 5) scal[tid] = 0;
+        __syncthreads();
+    }
+    for (int base = 0; base < m; base += nt) {
+        const int i = base + tid;
         unsigned long long k = ~0ull;
+        float d = INFINITY;
         if (i < count) {
             const float x = ex[i];
             if (!marker || x >= 0.0f) {
                 const float dx = x - lx, dy = ey[i] - ly;
-                const float d = sqrtf(dx * dx + dy * dy);
+                d = sqrtf(dx * dx + dy * dy);
                 k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
             }
         }
-        key[i] = k;
+        if (i < m) key[i] = k;
+        if (preselect) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned b = __ballot_sync(FULL, d <= rad[q]);
+                if (lane == 0 && b) atomicAdd(&scal[q], __popc(b));
+            }
+        }
     }
     __syncthreads();
-    bitonic_sort_u64(key, m);
+    unsigned long long* sorted = key;
+    int ms = m;
+    if (preselect) {
+        int sel = -1;
+#pragma unroll
+        for (int q = 3; q >= 0; --q)
+            if (scal[q] >= n && scal[q] <= RAM_CAND_CAP) sel = q;  // smallest sufficient radius
+        if (sel >= 0) {  // block-uniform
+            const unsigned lim = __float_as_uint(rad[sel]);
+            ms = 1;
+            while (ms < scal[sel]) ms <<= 1;
+            for (int i = tid; i < ms; i += nt) cand[i] = ~0ull;
+            __syncthreads();
+            for (int i = tid; i < m; i += nt) {
+                const unsigned long long k = key[i];
+                if ((unsigned)(k >> 32) <= lim) cand[atomicAdd(&scal[4], 1)] = k;  // order is fixed by the sort
+            }
+            __syncthreads();
+            sorted = cand;
+        }
+    }
+    bitonic_sort_u64(sorted, ms);
     for (int r = tid; r < n; r += nt) {
         float ox = 0.0f, oy = 0.0f;
-        if (r < m && key[r] != ~0ull) {
-            const int i = (int)(unsigned)key[r];
+        if (r < ms && sorted[r] != ~0ull) {
+            const int i = (int)(unsigned)sorted[r];
             ox = ex[i] - lx; oy = ey[i] - ly;
         }
         out[2 * r] = ox; out[2 * r + 1] = oy;
@@ -148,12 +193,14 @@ __device__ void ram_player_cells(const float* cx, const float* cy, const float* 
     for (int r = nsel * 5 + lane; r < n * 5; r += 32) out[r] = 0.0f;
 }
 
-// grid = (arenas * agents); block = 128; dynamic smem = sort_cap * 8 + 64 * 8 bytes.
+// grid = (arenas * agents); block = 128; dynamic smem = (sort_cap + 64 + RAM_CAND_CAP) * 8 bytes.
 __global__ void __launch_bounds__(128) ram_features_kernel(const __grid_constant__ DevParams p, const __grid_constant__ RamParams rp,
                                                            const float* __restrict__ state, float* __restrict__ out_all) {
     extern __shared__ __align__(16) unsigned long long ram_smem[];
     unsigned long long* key = ram_smem;              // [sort_cap]
     unsigned long long* pkey = ram_smem + rp.sort_cap;  // [64] other players by distance
+    unsigned long long* cand = pkey + 64;            // [RAM_CAND_CAP] preselected candidates
+    __shared__ int s_scal[8];
     __shared__ float s_loc[2];
     __shared__ int s_has;
     const AgarLayout& L = p.L;
@@ -180,11 +227,11 @@ __global__ void __launch_bounds__(128) ram_features_kernel(const __grid_constant
     }
     const float lx = s_loc[0], ly = s_loc[1];
     int off = 0;
-    ram_nearest_points(key, rp.sort_cap, rec + L.pellet_x, rec + L.pellet_y, p.c.num_pellets, true, lx, ly, rp.n_pellet, out + off);
+    ram_nearest_points(key, cand, s_scal, rp.sort_cap, rec + L.pellet_x, rec + L.pellet_y, p.c.num_pellets, true, lx, ly, rp.n_pellet, p.c.arena_size, out + off);
     off += 2 * rp.n_pellet;
-    ram_nearest_points(key, rp.sort_cap, rec + L.virus_x, rec + L.virus_y, p.c.num_viruses, false, lx, ly, rp.n_virus, out + off);
+    ram_nearest_points(key, cand, s_scal, rp.sort_cap, rec + L.virus_x, rec + L.virus_y, p.c.num_viruses, false, lx, ly, rp.n_virus, p.c.arena_size, out + off);
     off += 2 * rp.n_virus;
-    ram_nearest_points(key, rp.sort_cap, rec + L.food_x, rec + L.food_y, p.c.max_foods, true, lx, ly, rp.n_food, out + off);
+    ram_nearest_points(key, cand, s_scal, rp.sort_cap, rec + L.food_x, rec + L.food_y, p.c.max_foods, true, lx, ly, rp.n_food, p.c.arena_size, out + off);
     off += 2 * rp.n_food;
     // the agent's own cells: absolute coordinates (relative=False, :131)
     if (warp == 0)
