@@ -577,3 +577,13 @@ def test_step_host_chunked_path_equals_device_step(oracle):
         assert np.array_equal(obs, o.cpu().numpy()) and np.array_equal(rew, r.cpu().numpy()) and np.array_equal(done, d.cpu().numpy())
     assert torch.equal(e1.get_state(), e2.get_state())
     e1.close(); e2.close()
+
+
+def test_random_configs_fuzz(oracle):
+    """Differential fuzzing (tests/fuzz_parity.py): random sizes, grids, channel sets, thresholds, tick counts, arena
+    id bases; state, observations, rewards, dones, event multisets and RAM features bit-equal to the oracle."""
+    import fuzz_parity
+    rng = np.random.default_rng(2024)
+    for i in range(40):
+        kw = fuzz_parity.random_config(rng)
+        fuzz_parity.run_one(kw, int(rng.integers(0, 2 ** 31)), 25, rng)
