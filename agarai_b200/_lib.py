@@ -66,6 +66,7 @@ SYMBOLS = [
     ("agar_screen_gray", C.c_int, [_P, C.c_int64, _P, C.c_int32, _P]),
     ("agar_launch_count", C.c_int64, [_P]),
     ("agar_kernel_variant", C.c_char_p, [_P]),
+    ("agar_step_smem_bytes", C.c_int64, [C.POINTER(AgarConfig)]),
 ]
 
 _lib = None
@@ -75,22 +76,27 @@ class AgarError(RuntimeError):
     pass
 
 
+def load(path):
+    """Load one build of the CUDA library (the default one, or a specialised copy from build.build_specialised)."""
+    if not os.path.exists(path):
+        raise AgarError(
+            f"{path} is missing: build it with `python -m agarai_b200.build` "
+            "(nvcc, sm_100a). agarai_b200 has no CPU fallback.")
+    L = C.CDLL(path)
+    for name, res, args in SYMBOLS:
+        fn = getattr(L, name)  # AttributeError here means header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if L.agar_abi_version() != 1:
+        raise AgarError("libagar_b200.so ABI version mismatch")
+    return L
+
+
 def lib():
     """Load the CUDA library; raises if it has not been built (no fallback exists)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise AgarError(
-                f"{LIB_PATH} is missing: build it with `python -m agarai_b200.build` "
-                "(nvcc, sm_100a). agarai_b200 has no CPU fallback.")
-        L = C.CDLL(LIB_PATH)
-        for name, res, args in SYMBOLS:
-            fn = getattr(L, name)  # AttributeError here means header and library disagree
-            fn.restype = res
-            fn.argtypes = args
-        if L.agar_abi_version() != 1:
-            raise AgarError("libagar_b200.so ABI version mismatch")
-        _lib = L
+        _lib = load(LIB_PATH)
     return _lib
 
 

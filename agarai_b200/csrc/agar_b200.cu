@@ -43,6 +43,11 @@ using CvCfg4 = StCfg<16, 0, 1000, 0, 64, 64, 7, 4>;   // configs[3]: 16 agents p
 using CvA2C = StCfg<32, 0, 1000, 25, 64, 32, 15, 4>;     // a2c/hyperparameters.py:89-107: 32 agents, 25 viruses, grid 32
 using CvA2CTest = StCfg<8, 25, 1000, 25, 64, 32, 15, 4>; // a2c/train.py:17-34: 8 agents + 25 bots
 using CvDQN = StCfg<1, 0, 30, 0, 64, 128, 15, 4>;        // dqn/hyperparameters.py:23-28,97-104: arena 45, 30 pellets, grid 128
+#ifdef AGAR_EXTRA_CV
+// one more world, given on the compiler command line: agarai_b200.build.build_specialised(cfg) compiles a copy of
+// the library with -DAGAR_EXTRA_CV -DAGAR_EXTRA_A=.. -DAGAR_EXTRA_BOTS=.. ... for a config outside the list above
+using CvExtra = StCfg<AGAR_EXTRA_A, AGAR_EXTRA_BOTS, AGAR_EXTRA_P, AGAR_EXTRA_V, AGAR_EXTRA_F, AGAR_EXTRA_G, AGAR_EXTRA_FLAGS, AGAR_EXTRA_TICKS>;
+#endif
 
 template <class CV>
 bool matches(const AgarConfig& c, const AgarLayout& L) {
@@ -170,6 +175,10 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
         if (v >= 5 && v <= 8) e->min_blocks = v;
     }
     const bool generic_only = std::getenv("AGAR_GENERIC_KERNEL") != nullptr;  // tuning/test switch: never specialise
+#ifdef AGAR_EXTRA_CV
+    // a per-config copy of the library (build.build_specialised) carries only its own specialisation
+    if (!generic_only && matches<CvExtra>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, AGAR_EXTRA_CV_BLOCKS, CvExtra>; e->kernel_name = "extra"; }
+#else
     if (!generic_only && matches<CvCfg2>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 7, CvCfg2>; e->kernel_name = "cfg2"; }
     else if (!generic_only && matches<CvCfg1>(*cfg, p.L)) {
         e->kernel_name = "cfg1";
@@ -181,6 +190,7 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
     else if (!generic_only && matches<CvA2C>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 6, CvA2C>; e->kernel_name = "a2c"; }
     else if (!generic_only && matches<CvA2CTest>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 6, CvA2CTest>; e->kernel_name = "a2c_test"; }
     else if (!generic_only && matches<CvDQN>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 8, CvDQN>; e->kernel_name = "dqn"; }
+#endif
     else {
         e->kernel_name = "generic";
         switch (e->min_blocks) {
@@ -458,6 +468,13 @@ int agar_screen_gray(const uint8_t* d_rgb, int64_t n_pixels, void* d_out, int32_
 
 int64_t agar_launch_count(const AgarEnv* e) { return e ? e->launches : 0; }
 const char* agar_kernel_variant(const AgarEnv* e) { return e ? e->kernel_name : ""; }
+
+int64_t agar_step_smem_bytes(const AgarConfig* cfg) {
+    if (!cfg || agar_spec_config_check(cfg)) return -1;
+    AgarLayout L;
+    agar_spec_layout(cfg, &L);
+    return (int64_t)smem_bytes(L, cfg->grid_size);
+}
 
 #ifdef AGAR_PHASE_CLOCKS
 // tuning builds only (not declared in the header): cycles charged to each phase id since the last call

@@ -115,12 +115,12 @@ class BatchedAgarioEnv:
     metadata = {"render.modes": []}
 
     def __init__(self, cfg: "_lib.AgarConfig", device=None, seed: int = 0, action_config: ActionConfig = None,
-                 observation: str = "grid", ram_extractor=None):
+                 observation: str = "grid", ram_extractor=None, lib_path: Optional[str] = None):
         self._h = None
         if observation not in ("grid", "ram"):
             raise ValueError("observation must be 'grid' or 'ram'")
         self.observation = observation
-        self._L = _lib.lib()
+        self._L = _lib.lib() if lib_path is None else _lib.load(lib_path)  # lib_path: a build.build_specialised() copy
         if not torch.cuda.is_available():
             raise _lib.AgarError("BatchedAgarioEnv needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -357,9 +357,15 @@ def make(env_id: str = "agario-grid-v0", num_envs: int = 1, device=None, seed: i
         raise ValueError(f"unknown env id {env_id!r}")
     multi_agent = bool(kwargs.get("multi_agent", True))
     ram_extractor = kwargs.pop("ram_extractor", None)
+    specialise = bool(kwargs.pop("specialise", False))
     cfg = config_from_gym_kwargs(num_envs=num_envs, **kwargs)
+    lib_path = None
+    if specialise and cfg.event_capacity == 0:  # compile (once) a step kernel with this world's sizes as constants
+        from . import build as _build
+        lib_path = _build.build_specialised(cfg)
     env = BatchedAgarioEnv(cfg, device=device, seed=seed, action_config=action_config,
-                           observation="ram" if env_id == "agario-ram-v0" else "grid", ram_extractor=ram_extractor)
+                           observation="ram" if env_id == "agario-ram-v0" else "grid", ram_extractor=ram_extractor,
+                           lib_path=lib_path)
     if gym_compat is None:
         gym_compat = num_envs == 1
     return GymCompatEnv(env, multi_agent=multi_agent) if gym_compat else env

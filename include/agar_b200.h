@@ -269,6 +269,8 @@ int64_t agar_launch_count(const AgarEnv* env);
 /* which instantiation of the step kernel the handle launches: "generic" (sizes read at run time) or the name of a
  * compile-time specialised world ("cfg1", "cfg2", "cfg4", "a2c", "a2c_test", "dqn") */
 const char* agar_kernel_variant(const AgarEnv* env);
+/* dynamic shared memory one CTA of the step kernel needs for this config (bytes; -1 for a bad config) */
+int64_t agar_step_smem_bytes(const AgarConfig* cfg);
 
 #ifdef __cplusplus
 }

@@ -587,3 +587,28 @@ def test_random_configs_fuzz(oracle):
     for i in range(40):
         kw = fuzz_parity.random_config(rng)
         fuzz_parity.run_one(kw, int(rng.integers(0, 2 ** 31)), 25, rng)
+
+
+def test_per_config_specialised_library_build(oracle):
+    """build.build_specialised / make(..., specialise=True): a copy of the library whose step kernel has an
+    arbitrary config's sizes as compile-time constants (nvcc at run time, cached in-tree) equals the oracle."""
+    import shutil
+    import agarai_b200 as ab
+    if not (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        pytest.skip("nvcc is not on this machine")
+    kw = dict(num_agents=2, num_bots=3, num_pellets=500, num_viruses=5, arena_size=200.0, grid_size=32,
+              observe_viruses=True, difficulty="normal")
+    env = ab.make("agario-grid-v0", num_envs=9, seed=12, specialise=True, gym_compat=False, **kw)
+    assert env.kernel_variant == "extra"
+    ocfg = oracle.default_config(**{n: getattr(env.cfg, n) for n, _ in type(env.cfg)._fields_})
+    oenv = oracle.OracleEnv(ocfg, seed=12, nthreads=4)
+    assert np.array_equal(env.reset().cpu().numpy(), oenv.reset())
+    rng = np.random.default_rng(4)
+    for t in range(40):
+        xy, act = random_actions(rng, 9, 2, (0, 1, 2), 0.5)
+        o, r, d, _ = env.step(torch.from_numpy(xy).cuda(), torch.from_numpy(act).cuda())
+        oo, orr, od = oenv.step(xy, act)
+        assert np.array_equal(o.cpu().numpy().view(np.int32), oo.view(np.int32)) and np.array_equal(r.cpu().numpy(), orr)
+        assert np.array_equal(d.cpu().numpy(), od)
+    assert np.array_equal(env.get_state().cpu().numpy().view(np.int32), oenv.get_state().view(np.int32))
+    env.close()
