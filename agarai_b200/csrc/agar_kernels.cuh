@@ -2,7 +2,8 @@
 //
 // One CTA owns one arena for one env step: it stages the arena's whole state record in shared
 // memory, runs ticks_per_step ticks there, writes back only what changed and rasterises the
-// grid observations straight from shared memory with 128-bit streaming stores.  The rules are
+// grid observations straight from shared memory (base image from registers with 128-bit stores,
+// occupied bins patched in place).  The rules are
 // those of DESIGN.md §3; the sequential definition is oracle/agar_oracle.c and the two must
 // agree bit for bit, so every float expression here is written as single IEEE operations in
 // the same order (the file is compiled with -fmad=false; sqrtf and '/' are the correctly
@@ -857,15 +858,16 @@ __device__ __noinline__ void virus_pops(const DevParams& p, const KArgs& a, int 
 // grid = number of arenas (records); block = kThreads; dynamic smem = smem_bytes().
 //
 // Phase plan of one step (B = __syncthreads):
-//   stage record | B | pellet hash (counting sort) | alive list + player masks | B | players:
-//   respawn, centroid, targets | B | bots pick targets through the hash, split, feed | B |
-//   per tick:  motion + pellet query (one thread per alive cell, hash neighbourhood + extras) | B |
-//              resolve claimed pellets (count, respawn by Philox, extras) | B |
-//              apply gains + virus claims | B | [pops] | cell-eats-cell test | B | [apply] |
-//              merge (half-warp per player, shuffles) | B
-//   rewards/dones | B | write back | raster.
-// kMinBlocks is chosen by the host from the shared-memory footprint (CTAs that fit per SM) so that the
-// register budget never becomes the occupancy limit: 5 -> <=100 regs, 6 -> <=80, 7 -> <=72.
+//   stage record + persisted hash (TMA bulk copies) | B | [pellet hash rebuild] | alive list + player masks | B |
+//   players: respawn, centroid | B | agents: action -> target; bots: nearest pellet through the hash | B |
+//   [split] [feed] | B |
+//   per tick:  motion + pellet query (four lanes per alive cell, hash rows + respawn list) | B |
+//              [resolve claimed pellets: count, respawn by Philox, respawn list | B] | [foods] |
+//              apply gains + virus claims, cell-eats-cell test | B | [pops, test again] | [ordered gains] |
+//              [merge (half-warp per player, shuffles) | B]
+//   rewards/dones | B | [auto reset] | persist hash | write back (bulk store) | raster.
+// kMinBlocks is the CTAs-per-SM bound of the instantiation (chosen by the host from the shared-memory footprint),
+// i.e. the register budget: 5 -> <=100 registers, 6 -> <=80, 7 -> <=72, 8 -> 64, 10 -> <=51.  CV is the config view.
 template <int kThreads, int kMinBlocks, class CV>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const __grid_constant__ DevParams p,
                                                                const __grid_constant__ KArgs a) {
