@@ -263,12 +263,16 @@ __device__ __forceinline__ float hw_treesum(float v) {
 }
 
 // ------------------------------------------------------------------------- shared memory map
-// Pellet hash: HASH_W x HASH_W uniform grid over the arena, built by counting sort once per step
-// (and again only if more than EXTRA_CAP pellets respawned since).
+// Pellet hash: HASH_W x HASH_W uniform grid over the arena, built by counting sort (`sorted` holds the pellet ids
+// bin after bin, `hstart` the first slot of each bin's run).  Every run is built with HASH_SLACK free slots
+// (0xFFFF) behind its pellets, so the hash is kept current instead of rebuilt: a respawning pellet's old entry is
+// turned into a free slot and the pellet takes a free slot of its new bin; only a bin without a free slot forces a
+// rebuild (next tick).  Readers skip free slots.  The hash is persisted across steps in a side buffer.
 #define HASH_W 16
 #define HASH_BINS (HASH_W * HASH_W)
-#define EXTRA_CAP 16    // pellets that may respawn before the hash is rebuilt (each is checked by every cell)
-#define HASH_HDR 4      // words of the persisted hash header: {epoch, nextras, 0, 0}
+#define HASH_SLACK 2    // free slots per bin at build time
+#define HASH_FREE 0xFFFFu
+#define HASH_HDR 4      // words of the persisted hash header: {epoch, 0, 0, 0}
 #define HITS_CAP 128    // claimed pellets listed per tick
 
 struct Smem {
@@ -276,11 +280,9 @@ struct Smem {
     int32_t* reci;    // same, as int32
     // pellet hash, kept through the raster
     int32_t* hstart;  // [HASH_BINS+1] first sorted position of each bin
-    uint16_t* sorted; // [P_pad]       pellet ids in bin order
-    uint16_t* extras; // [EXTRA_CAP]   pellets respawned since the hash was built (unique)
-    int32_t* hhdr;    // [HASH_HDR]    header of the persisted hash record: {epoch, nextras, 0, 0}
+    uint16_t* sorted; // [sort_slots]  pellet ids in bin order, HASH_FREE = free slot
+    int32_t* hhdr;    // [HASH_HDR]    header of the persisted hash record: {epoch, 0, 0, 0}
     uint64_t* mbar;   // mbarrier for the bulk copies (2 words)
-    int32_t* isx;     // [P_pad/32+1]  bit per pellet: respawned since the hash was built
     // per-tick scratch
     int32_t* hcur;    // [HASH_BINS]   counting-sort cursors (only while the hash is built)
     uint16_t* pwin;   // [P_pad]       winner cell of each pellet this tick (16-bit CAS-min), NONE16 = unclaimed
@@ -295,11 +297,11 @@ struct Smem {
     int32_t *palive, *pmask;                         // [K_pad]
     float *dirx, *diry, *mass0;                      // [A_pad] (agents only)
     int32_t* pact;                                   // [A_pad]
-    int32_t* rb;                                     // [96] raster: other players' cells in view
+    int32_t* rb;                                     // [96] raster: other players' cells in view (aliases hcur)
     int32_t* sc;                                     // [32] scalars + [32] list-membership bitmask
 };
 enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT, SC_EVCOUNT, SC_RESET, SC_ALLDONE,
-       SC_NHITS, SC_NEXTRAS, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NOB, SC_HBUILT, SC_NEX0, SC_COUNT };
+       SC_NHITS, SC_HDIRTY, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NOB, SC_HBUILT, SC_COUNT };
 static_assert(SC_COUNT <= 32, "scalar slots overlap the list-membership bitmask");
 
 __host__ __device__ inline size_t pad4z(size_t n) { return (n + 3) & ~(size_t)3; }
@@ -321,10 +323,15 @@ __host__ __device__ inline size_t union_words(const LT& L, int G) {
 template <class LT>
 __host__ __device__ inline size_t kpad(const LT& L) { return pad4z((size_t)L.num_players); }
 
-// persisted hash record: the shared-memory block [hstart | sorted | extras] followed by the header
+// slots of `sorted`: every pellet plus the slack of every bin (a multiple of 8 so that the words divide by 4)
+template <class LT>
+__host__ __device__ inline size_t sort_slots(const LT& L) {
+    return ((size_t)L.P_pad + HASH_SLACK * HASH_BINS + 7) & ~(size_t)7;
+}
+// persisted hash record: the shared-memory block [hstart | sorted] followed by the header
 template <class LT>
 __host__ __device__ inline size_t hash_body_words(const LT& L) {
-    return HASH_BINS + 4 + pad4z((size_t)L.P_pad / 2) + EXTRA_CAP / 2;
+    return HASH_BINS + 4 + sort_slots(L) / 2;
 }
 template <class LT>
 __host__ __device__ inline size_t hash_record_words(const LT& L) { return hash_body_words(L) + HASH_HDR; }
@@ -333,11 +340,10 @@ template <class LT>
 __host__ __device__ inline size_t smem_bytes(const LT& L, int G) {
     size_t w = 0;
     w += (size_t)L.words;                                   // rec
-    w += HASH_BINS + 4 + pad4z((size_t)L.P_pad / 2) + EXTRA_CAP / 2 + HASH_HDR + 4 + pad4z((size_t)L.P_pad / 32 + 1);  // hash kept, header, mbarrier
+    w += hash_body_words(L) + HASH_HDR + 4;                 // hash kept, header, mbarrier
     w += union_words(L, G);                                 // per-tick scratch
     w += (size_t)(L.V_pad + 4);                             // vwin
     w += kpad(L) * 6 + (size_t)L.A_pad * 4;                 // per-player and per-agent arrays
-    w += 96;                                                // raster buffers
     w += 64;                                                // scalars + alive-list membership bits
     return w * 4 + 16;
 }
@@ -348,14 +354,12 @@ __device__ __forceinline__ Smem carve(float* base, const LT& L, int G) {
     float* p = base;
     s.rec = p; s.reci = (int32_t*)p; p += L.words;           // words % 4 == 0
     s.hstart = (int32_t*)p; p += HASH_BINS + 4;
-    s.sorted = (uint16_t*)p; p += pad4z((size_t)L.P_pad / 2);
-    s.extras = (uint16_t*)p; p += EXTRA_CAP / 2;
+    s.sorted = (uint16_t*)p; p += sort_slots(L) / 2;
     s.hhdr = (int32_t*)p; p += HASH_HDR;                     // contiguous with the body: one bulk copy
     s.mbar = (uint64_t*)p; p += 4;
-    s.isx = (int32_t*)p; p += pad4z((size_t)L.P_pad / 32 + 1);
     {
         int32_t* h = (int32_t*)p;
-        s.hcur = h; h += HASH_BINS;
+        s.hcur = h; s.rb = h; h += HASH_BINS;                // rb: raster scratch, used when no hash is being built
         s.pwin = (uint16_t*)h; h += L.P_pad / 2;
         s.hits = (uint16_t*)h; h += HITS_CAP / 2;
         s.list = (uint16_t*)h; h += L.cells_total / 2;
@@ -370,7 +374,6 @@ __device__ __forceinline__ Smem carve(float* base, const LT& L, int G) {
     s.palive = (int32_t*)p; p += kp; s.pmask = (int32_t*)p; p += kp;
     s.dirx = p; p += L.A_pad; s.diry = p; p += L.A_pad; s.mass0 = p; p += L.A_pad;
     s.pact = (int32_t*)p; p += L.A_pad;
-    s.rb = (int32_t*)p; p += 96;
     s.sc = (int32_t*)p; p += 64;
     return s;
 }
@@ -434,7 +437,8 @@ __device__ __forceinline__ int hash_coord(const DevParams& p, float v) {
     return b < 0 ? 0 : (b > HASH_W - 1 ? HASH_W - 1 : b);
 }
 
-// counting sort of the present pellets into the HASH_W x HASH_W grid (all threads; ends synchronised).
+// counting sort of the present pellets into the HASH_W x HASH_W grid, HASH_SLACK free slots behind every bin's
+// pellets (all threads; ends synchronised).
 // Order inside a bin is arbitrary: every consumer reduces with min / integer counts.
 // Out of line: with the hash persisted across steps this runs only after resets and respawn overflows.
 template <class CV>
@@ -445,7 +449,7 @@ __device__ __noinline__ void build_hash(const DevParams& p) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, P = CV_INT(P, p.c.num_pellets);
     const float* px = s.rec + L.pellet_x; const float* py = s.rec + L.pellet_y;
     for (int i = tid; i < HASH_BINS; i += nt) s.hcur[i] = 0;
-    for (int i = tid; i < L.P_pad / 32 + 1; i += nt) s.isx[i] = 0;
+    for (int i = tid; i < (int)sort_slots(L) / 2; i += nt) reinterpret_cast<uint32_t*>(s.sorted)[i] = 0xFFFFFFFFu;  // all free
     __syncthreads();
     for (int i = tid; i < P; i += nt) {
         const float x = px[i];
@@ -458,7 +462,7 @@ __device__ __noinline__ void build_hash(const DevParams& p) {
         constexpr int PER = HASH_BINS / 32;
         int c[PER], tot = 0;
 #pragma unroll
-        for (int q = 0; q < PER; ++q) { c[q] = s.hcur[lane * PER + q]; tot += c[q]; }
+        for (int q = 0; q < PER; ++q) { c[q] = s.hcur[lane * PER + q] + HASH_SLACK; tot += c[q]; }  // run = pellets + slack
         int incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -469,7 +473,7 @@ __device__ __noinline__ void build_hash(const DevParams& p) {
 #pragma unroll
         for (int q = 0; q < PER; ++q) { s.hstart[lane * PER + q] = run; s.hcur[lane * PER + q] = run; run += c[q]; }
         if (lane == 31) s.hstart[HASH_BINS] = incl;
-        if (lane == 0) { s.sc[SC_NEXTRAS] = 0; s.sc[SC_REBUILD] = 0; s.sc[SC_NHITS] = 0; s.sc[SC_HASHOK] = 1; s.sc[SC_HBUILT] = 1; }
+        if (lane == 0) { s.sc[SC_REBUILD] = 0; s.sc[SC_NHITS] = 0; s.sc[SC_HASHOK] = 1; s.sc[SC_HBUILT] = 1; }
     }
     __syncthreads();
     for (int i = tid; i < P; i += nt) {
@@ -477,6 +481,23 @@ __device__ __noinline__ void build_hash(const DevParams& p) {
         if (b != 0xFFFF) { s.sorted[atomicAdd(&s.hcur[b], 1)] = (uint16_t)i; s.pwin[i] = NONE16; }
     }
     __syncthreads();
+}
+
+// A pellet left position (x0, y0): its entry in that bin's run becomes a free slot (one thread per pellet).
+__device__ __forceinline__ void hash_remove(const DevParams& p, const Smem& s, int i, float x0, float y0) {
+    const int b = hash_coord(p, y0) * HASH_W + hash_coord(p, x0);
+    for (int j = s.hstart[b], j1 = s.hstart[b + 1]; j < j1; ++j)
+        if (s.sorted[j] == (uint16_t)i) { s.sorted[j] = (uint16_t)HASH_FREE; return; }
+}
+// ... and appeared at (x1, y1): it takes a free slot of that bin's run; false if the bin has none (rebuild needed).
+// Several threads may insert into one bin at once: slots are claimed with a 16-bit compare-and-swap.
+__device__ __forceinline__ bool hash_insert(const DevParams& p, const Smem& s, int i, float x1, float y1) {
+    const int b = hash_coord(p, y1) * HASH_W + hash_coord(p, x1);
+    for (int j = s.hstart[b], j1 = s.hstart[b + 1]; j < j1; ++j)
+        if (s.sorted[j] == (uint16_t)HASH_FREE &&
+            atomicCAS(reinterpret_cast<unsigned short*>(&s.sorted[j]), (unsigned short)HASH_FREE, (unsigned short)i) == (unsigned short)HASH_FREE)
+            return true;
+    return false;
 }
 
 // all threads: unordered list of the alive cells' gids, per-player alive masks, "some player has
@@ -733,8 +754,7 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
             if (ch_pel >= 0) {
                 float* chan = out_a + (size_t)ch_pel * GG;
                 if (use_hash) {
-                    // pellets under the view window: hash rows (one warp per row), skipping entries that
-                    // respawned since the hash was built; those come from the respawn list instead
+                    // pellets under the view window: the hash rows
                     const int bx0 = hash_coord(p, cx - lim), bx1 = hash_coord(p, cx + lim);
                     const int by0 = hash_coord(p, cy - lim), by1 = hash_coord(p, cy + lim);
                     // warp 0 is busy with the mass patches above: the other warps share the hash rows
@@ -743,16 +763,9 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
                         const int j1 = s.hstart[by * HASH_W + bx1 + 1];
                         for (int j = s.hstart[by * HASH_W + bx0] + lane; j < j1; j += 32) {
                             const int i = s.sorted[j];
-                            if ((s.isx[i >> 5] >> (i & 31)) & 1) continue;
-                            const float x = px[i];
-                            if (!(x >= 0.0f)) continue;
-                            count_entity(p, chan, x, py[i], cx, cy, G, half, lim);
+                            if (i == (int)HASH_FREE) continue;
+                            count_entity(p, chan, px[i], py[i], cx, cy, G, half, lim);  // every present pellet has exactly one entry
                         }
-                    }
-                    const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
-                    for (int e = tid; e < nex; e += nt) {
-                        const int i = s.extras[e];
-                        count_entity(p, chan, px[i], py[i], cx, cy, G, half, lim);
                     }
                 } else {
                     for (int i = tid; i < CV_INT(P, p.c.num_pellets); i += nt) {
@@ -910,7 +923,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         if (tid < 64) s.sc[tid] = 0;
         if (a.flags & F_STEP) {
             for (int i = tid; i < L.P_pad / 2; i += nt) reinterpret_cast<uint32_t*>(s.pwin)[i] = 0xFFFFFFFFu;
-            for (int i = tid; i < L.P_pad / 32 + 1; i += nt) s.isx[i] = 0;
         }
     }
     mbar_wait(s.mbar, 0);
@@ -920,6 +932,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     if (load_hash) hhdr = *reinterpret_cast<const int4*>(s.hhdr);
 
     bool static_dirty = false;  // whole record must be written back (after a reset)
+    int persist_hash = 0;       // 0: the persisted hash is current, 1: its slot order changed, 2: rebuilt
     if (a.flags & F_RESET) {
         if (!a.reset_mask || a.reset_mask[arena]) { reset_arena<CV>(p, gid_lo, gid_hi); static_dirty = true; }
     }
@@ -929,9 +942,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         PHASE(0);  // staging
         // ---- pellet hash (persisted across steps, rebuilt when stale), alive list ----
         if (load_hash && hhdr.x == p.hash_epoch) {
-            const int nex = min(hhdr.y, EXTRA_CAP);
-            if (tid < nex) { const int i = s.extras[tid]; atomicOr(&s.isx[i >> 5], 1 << (i & 31)); }
-            if (tid == 0) { s.sc[SC_NEXTRAS] = nex; s.sc[SC_NEX0] = nex; s.sc[SC_HASHOK] = 1; }
+            if (tid == 0) s.sc[SC_HASHOK] = 1;
         } else {
             build_hash<CV>(p);
         }
@@ -1014,27 +1025,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 const int bx = hash_coord(p, Cx), by = hash_coord(p, Cy);
                 int x0 = max(bx - 1, 0), x1 = min(bx + 1, HASH_W - 1), y0 = max(by - 1, 0), y1 = min(by + 1, HASH_W - 1);
                 float best = INFINITY; int bi = NONE_I;
-                const int nex = s.sc[SC_NEXTRAS];  // pellets that moved since the hash was built: always examined
                 for (int pass = 0; pass < 2; ++pass) {
                     for (int row = y0; row <= y1; ++row) {
                         const int j1 = s.hstart[row * HASH_W + x1 + 1];
                         for (int j = s.hstart[row * HASH_W + x0] + l4; j < j1; j += 4) {
-                            const int i = s.sorted[j];  // an entry of a pellet that respawned since the build is harmless:
-                            const float qx = px[i];     // it is judged at its true position (and again from the respawn list)
-                            if (!(qx >= 0.0f)) continue;
-                            float dx = qx - Cx, dy = py[i] - Cy;
+                            const int i = s.sorted[j];
+                            if (i == (int)HASH_FREE) continue;
+                            float dx = px[i] - Cx, dy = py[i] - Cy;
                             if (fabsf(dx) <= R && fabsf(dy) <= R) {
                                 float d2 = dx * dx + dy * dy;
                                 if (d2 < best || (d2 == best && i < bi)) { best = d2; bi = i; }
                             }
-                        }
-                    }
-                    for (int e = l4; e < nex; e += 4) {
-                        const int i = s.extras[e];
-                        float dx = px[i] - Cx, dy = py[i] - Cy;
-                        if (fabsf(dx) <= R && fabsf(dy) <= R) {
-                            float d2 = dx * dx + dy * dy;
-                            if (d2 < best || (d2 == best && i < bi)) { best = d2; bi = i; }
                         }
                     }
 #pragma unroll
@@ -1144,7 +1145,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             //      with atomicMin: the lowest gid wins ----
             {
                 const int n = s.sc[SC_NLIST];
-                const int nex = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
                 const int l4 = lane & 3;
                 for (int qb = (tid >> 5) * 8; qb < n; qb += nt >> 2) {  // 8 cells per warp pass, warp-uniform
                     const int q = qb + (lane >> 2);
@@ -1177,18 +1177,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                         const int j1 = s.hstart[by * HASH_W + bx1 + 1];
                         for (int j = s.hstart[by * HASH_W + bx0] + l4; j < j1; j += 4) {
                             const int i = s.sorted[j];
-                            const float qx = px[i];
-                            if (!(qx >= 0.0f)) continue;
-                            const float ex = qx - x, ey = py[i] - y;
+                            if (i == (int)HASH_FREE) continue;
+                            const float ex = px[i] - x, ey = py[i] - y;
                             if (ex * ex + ey * ey < r2)
                                 if (claim_min16(&s.pwin[i], g)) { const int e = atomicAdd(&s.sc[SC_NHITS], 1); if (e < HITS_CAP) s.hits[e] = (uint16_t)i; }
                         }
-                    }
-                    for (int e = l4; e < nex; e += 4) {  // respawned since the hash was built (a stale hash
-                        const int i = s.extras[e];       // entry of the same pellet may claim twice: atomicMin dedups)
-                        const float ex = px[i] - x, ey = py[i] - y;
-                        if (ex * ex + ey * ey < r2)
-                            if (claim_min16(&s.pwin[i], g)) { const int e = atomicAdd(&s.sc[SC_NHITS], 1); if (e < HITS_CAP) s.hits[e] = (uint16_t)i; }
                     }
                 }
 #pragma unroll 1
@@ -1213,13 +1206,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     cnt_inc(s.cnt32, g);
                     ev_push<CV>(p, a, s, arena, tk, AGAR_EV_PELLET_EATEN, g, i);
                     float nx = -1.0f, ny = -1.0f;
+                    const bool hash_live = s.sc[SC_HASHOK] != 0;  // (it always is while ticks run; kept for safety)
+                    if (hash_live) hash_remove(p, s, i, px[i], py[i]);
                     if (c.pellet_regen) {
                         rand_pos(p, gid_lo, gid_hi, (uint32_t)i, AGAR_STREAM_PELLET_RESPAWN, tick, nx, ny);
-                        if (!(atomicOr(&s.isx[i >> 5], 1 << (i & 31)) & (1 << (i & 31)))) {  // first respawn since the build
-                            const int e = atomicAdd(&s.sc[SC_NEXTRAS], 1);
-                            if (e < EXTRA_CAP) s.extras[e] = (uint16_t)i; else s.sc[SC_REBUILD] = 1;
-                        }
+                        if (hash_live && !hash_insert(p, s, i, nx, ny)) s.sc[SC_REBUILD] = 1;  // its bin is full: rebuild next tick
                     }
+                    s.sc[SC_HDIRTY] = 1;
                     px[i] = nx; py[i] = ny;
                     if (!(a.flags & F_READONLY)) { grec[L.pellet_x + i] = nx; grec[L.pellet_y + i] = ny; }
                 }
@@ -1427,21 +1420,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             if (tid == 0) s.sc[SC_HASHOK] = 0;  // pellets were redrawn: the raster scans them all
         }
         PHASE(12);  // rewards, auto reset
-        // ---- persist the pellet hash for the next step ----
+        // ---- persist the pellet hash for the next step (the copy itself goes out with the record below) ----
         if (a.hash && !(a.flags & F_READONLY)) {
-            int4* gh = reinterpret_cast<int4*>(a.hash + (size_t)arena * hash_words);
-            const int body4 = (int)hash_body_words(L) / 4, ex4 = (HASH_BINS + 4 + (int)pad4z((size_t)L.P_pad / 2)) / 4;
-            const int4* src = reinterpret_cast<const int4*>(s.hstart);
-            const bool ok = s.sc[SC_HASHOK] != 0;
-            const int nexn = min(s.sc[SC_NEXTRAS], EXTRA_CAP);
-            if (ok && s.sc[SC_HBUILT]) {                   // rebuilt this step: bins + order + respawn list
-                for (int i = tid; i < body4; i += nt) gh[i] = src[i];
-            } else if (ok && nexn != s.sc[SC_NEX0]) {      // only the respawn list grew
-                for (int i = ex4 + tid; i < body4; i += nt) gh[i] = src[i];
-            }
-            const bool stale = !ok || s.sc[SC_REBUILD] != 0;  // redrawn pellets / overflowed list: rebuild next step
-            if (tid == 0 && (stale || s.sc[SC_HBUILT] || nexn != s.sc[SC_NEX0] || hhdr.x != p.hash_epoch))
-                gh[body4] = make_int4(stale ? 0 : p.hash_epoch, nexn, 0, 0);
+            const bool ok = s.sc[SC_HASHOK] != 0 && s.sc[SC_REBUILD] == 0;  // else redrawn pellets / a full bin: rebuild next step
+            persist_hash = !ok ? 0 : (s.sc[SC_HBUILT] ? 2 : (s.sc[SC_HDIRTY] ? 1 : 0));  // 2: bins + order, 1: order only
+            if (tid == 0 && (!ok || s.sc[SC_HBUILT] || hhdr.x != p.hash_epoch))
+                *reinterpret_cast<int4*>(a.hash + (size_t)arena * hash_words + hash_body_words(L)) = make_int4(ok ? p.hash_epoch : 0, 0, 0, 0);
         }
         if (!CV::is_static && c.event_capacity > 0 && tid == 0) a.ev_counts[arena] = s.sc[SC_EVCOUNT];
     }
@@ -1454,6 +1438,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         if (tid == 0) {
             fence_async_all();           // ... and ordered before the async proxy (shared and global)
             bulk_s2g(grec + w0, s.rec + w0, (uint32_t)(L.words - w0) * 4u);
+            if (persist_hash) {          // [hstart | sorted] or only the slots; the raster below only reads them
+                const int h0 = persist_hash == 2 ? 0 : HASH_BINS + 4;
+                bulk_s2g(a.hash + (size_t)arena * hash_words + h0, s.hstart + h0, (uint32_t)((int)hash_body_words(L) - h0) * 4u);
+            }
             bulk_commit();
         }
     }
