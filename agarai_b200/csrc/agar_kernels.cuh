@@ -301,7 +301,7 @@ struct Smem {
     int32_t* sc;                                     // [32] scalars + [32] list-membership bitmask
 };
 enum { SC_NLIST = 0, SC_ANYFEED, SC_ANYSPLIT, SC_FOODANY, SC_ANYEAT, SC_ANYVHIT, SC_EVCOUNT, SC_RESET, SC_ALLDONE,
-       SC_NHITS, SC_HDIRTY, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NOB, SC_HBUILT, SC_COUNT };
+       SC_NHITS, SC_HDIRTY, SC_REBUILD, SC_MULTI, SC_HASHOK, SC_NOB, SC_HBUILT, SC_MERGEABLE, SC_COUNT };
 static_assert(SC_COUNT <= 32, "scalar slots overlap the list-membership bitmask");
 
 __host__ __device__ inline size_t pad4z(size_t n) { return (n + 3) & ~(size_t)3; }
@@ -511,11 +511,13 @@ __device__ __forceinline__ void build_list(const DevParams& p, const Smem& s) {
         const int g = base + tid;
         const bool al = g < KC && s.rec[L.cell_m + g] > 0.0f;
         const unsigned b = __ballot_sync(0xffffffffu, al);
+        const unsigned rdy = __ballot_sync(0xffffffffu, al && s.rec[L.cell_t + g] == 0.0f);  // alive, merge timer run out
         if (lane == 0 && g < KC) s.sc[32 + (g >> 5)] = (int)b;  // membership bits of the list (sc[32..63])
         if (g < KC && (lane & 15) == 0) {
             unsigned hm = (b >> (lane & 16)) & 0xFFFFu;
             s.pmask[g >> 4] = (int)hm;
             if (__popc(hm) >= 2) s.sc[SC_MULTI] = 1;
+            if (__popc((rdy >> (lane & 16)) & 0xFFFFu) >= 2) s.sc[SC_MERGEABLE] = 1;  // the merge phase has work
         }
         if (b) {
             int pos = 0;
@@ -854,6 +856,7 @@ __device__ __noinline__ void virus_pops(const DevParams& p, const KArgs& a, int 
                     if (!(atomicOr(&inl[d >> 5], 1 << (d & 31)) & (1 << (d & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = (uint16_t)d;
                 }
                 s.sc[SC_MULTI] = 1;
+                if (!(c.merge_delay > 0.0f)) s.sc[SC_MERGEABLE] = 1;
             } else {
                 cm[g] = m1;
             }
@@ -1093,6 +1096,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     cm[d] = halfm; ct[d] = c.merge_delay;
                     ev_push<CV>(p, a, s, arena, 0, AGAR_EV_SPLIT, g, d);
                     s.sc[SC_MULTI] = 1;
+                    if (!(c.merge_delay > 0.0f)) s.sc[SC_MERGEABLE] = 1;
                     if (!(atomicOr(&inl[d >> 5], 1 << (d & 31)) & (1 << (d & 31)))) s.list[atomicAdd(&s.sc[SC_NLIST], 1)] = (uint16_t)d;
                 }
             }
@@ -1168,7 +1172,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     const float x = clampf(nx, 0.0f, arena_size), y = clampf(ny, 0.0f, arena_size);
                     if (l4 == 0) {
                         cx[g] = x; cy[g] = y; cix[g] = ix; ciy[g] = iy;
-                        if (t > 0.0f) ct[g] = t - 1.0f;
+                        if (t > 0.0f) {
+                            ct[g] = t - 1.0f;
+                            if (t - 1.0f == 0.0f) s.sc[SC_MERGEABLE] = 1;  // a merge becomes possible (conservative: set per cell)
+                        }
                     }
                     const float rp = r * 1.001f + 0.01f;
                     const int bx0 = hash_coord(p, x - rp), bx1 = hash_coord(p, x + rp);
@@ -1345,8 +1352,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 }
             }
             PHASE(10);  // eat apply
-            // ---- merge own cells whose timers ran out (half-warp per player, shuffles) ----
-            if (s.sc[SC_MULTI]) {
+            // ---- merge own cells whose timers ran out (half-warp per player, shuffles).  Skipped unless some player
+            //      held two cells with run-out timers at the start of the step or a timer ran out since ----
+            if (s.sc[SC_MULTI] && s.sc[SC_MERGEABLE]) {
                 for (int base = (tid & ~31); base < KC; base += nt) {
                     const int g = base + lane;
                     const bool valid = g < KC;
