@@ -586,7 +586,7 @@ __device__ __forceinline__ void count_entity(const DevParams& p, float* __restri
 // GridFeatureExtractor.extract for every agent of the arena held in s.rec
 // (features/extractors.py:39-96; oracle_grid_extract).  obs_arena points at [A,C,G,G].
 // use_hash: the pellet hash of this step is valid (pellets are then taken from the bins under
-// the view window plus the respawn list instead of scanning all of them).
+// the view window instead of scanning all of them).  nlist >= 0: the alive list of this step is valid.
 //
 // Every channel of an agent is the same base image — zeros, with -1 in the out-of-bounds rows and
 // columns — plus a few occupied bins.  The base image goes out from registers with 128-bit
@@ -596,7 +596,7 @@ __device__ __forceinline__ void count_entity(const DevParams& p, float* __restri
 // channels (pellets, viruses, foods) by float reductions of 1.0 in global memory, mass channels (own
 // cells, others) by warp 0 with sums taken in entity order.
 template <class CV>
-__device__ void raster_arena(const DevParams& p, const Smem& s, float* __restrict__ obs_arena, bool use_hash) {
+__device__ void raster_arena(const DevParams& p, const Smem& s, float* __restrict__ obs_arena, bool use_hash, int nlist) {
     decltype(auto) L = layout_of<CV>(p);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const int hbase = lane & 16, slot = lane & 15;
@@ -648,7 +648,10 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
         float* out_a = obs_arena + (size_t)a * C * GG;
         // ---- gather: other players' cells in view ----
         if (has && ch_others >= 0) {
-            for (int g = tid; g < KC; g += nt) {
+            // after a step the alive list names every cell that can exist (dead entries have mass 0); without one
+            // (observe-only calls, an arena just reset) every slot is examined
+            for (int q = tid; q < (nlist >= 0 ? nlist : KC); q += nt) {
+                const int g = nlist >= 0 ? (int)s.list[q] : q;
                 const float m = cm[g];
                 if (!(m > 0.0f) || (g >> 4) == a) continue;
                 const float dx = cxs[g] - cx, dy = cys[g] - cy;
@@ -1458,7 +1461,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     if ((a.flags & F_OBS) && a.obs) {
         __syncthreads();
         const int GG = G * G;
-        raster_arena<CV>(p, s, a.obs + (size_t)arena * A * CV_INT(C, p.C) * GG, s.sc[SC_HASHOK] != 0 && s.sc[SC_REBUILD] == 0);
+        raster_arena<CV>(p, s, a.obs + (size_t)arena * A * CV_INT(C, p.C) * GG, s.sc[SC_HASHOK] != 0 && s.sc[SC_REBUILD] == 0,
+                         ((a.flags & F_STEP) && !static_dirty && KC > 256) ? s.sc[SC_NLIST] : -1);  // (few slots: the scan is as fast)
     }
     PHASE(15);  // raster
     if (tid == 0) bulk_wait_read0();  // the bulk store must have read the record before the CTA exits
