@@ -500,30 +500,54 @@ __device__ __forceinline__ bool hash_insert(const DevParams& p, const Smem& s, i
     return false;
 }
 
-// all threads: unordered list of the alive cells' gids, per-player alive masks, "some player has
-// several cells" flag, list-membership bits.  SC_NLIST and SC_MULTI must be 0 on entry (a barrier earlier).
+// all threads: unordered list of the alive cells' gids, per-player alive masks, "some player has several cells" and
+// "a merge is possible" flags, list-membership bits.  SC_NLIST, SC_MULTI, SC_MERGEABLE must be 0 on entry (a barrier
+// earlier).  One thread takes four cell slots (128-bit loads of mass and merge timer): the four threads of a
+// player assemble its 16-bit masks by shuffles, eight threads a 32-bit membership word.
 template <class CV>
 __device__ __forceinline__ void build_list(const DevParams& p, const Smem& s) {
     decltype(auto) L = layout_of<CV>(p);
     const int KC = CV_INT(KC, p.KC);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-    for (int base = 0; base < KC; base += nt) {
-        const int g = base + tid;
-        const bool al = g < KC && s.rec[L.cell_m + g] > 0.0f;
-        const unsigned b = __ballot_sync(0xffffffffu, al);
-        const unsigned rdy = __ballot_sync(0xffffffffu, al && s.rec[L.cell_t + g] == 0.0f);  // alive, merge timer run out
-        if (lane == 0 && g < KC) s.sc[32 + (g >> 5)] = (int)b;  // membership bits of the list (sc[32..63])
-        if (g < KC && (lane & 15) == 0) {
-            unsigned hm = (b >> (lane & 16)) & 0xFFFFu;
-            s.pmask[g >> 4] = (int)hm;
-            if (__popc(hm) >= 2) s.sc[SC_MULTI] = 1;
-            if (__popc((rdy >> (lane & 16)) & 0xFFFFu) >= 2) s.sc[SC_MERGEABLE] = 1;  // the merge phase has work
+    const float4* m4 = reinterpret_cast<const float4*>(s.rec + L.cell_m);   // segments are 16-byte aligned, KC % 16 == 0
+    const float4* t4 = reinterpret_cast<const float4*>(s.rec + L.cell_t);
+    for (int base = 0; base < KC / 4; base += nt) {
+        const int q = base + tid;          // slots 4q .. 4q+3
+        const bool valid = q < KC / 4;
+        const float4 m = valid ? m4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 t = valid ? t4[q] : make_float4(1.f, 1.f, 1.f, 1.f);
+        const unsigned nib = (m.x > 0.0f ? 1u : 0u) | (m.y > 0.0f ? 2u : 0u) | (m.z > 0.0f ? 4u : 0u) | (m.w > 0.0f ? 8u : 0u);
+        const unsigned rdy = ((m.x > 0.0f && t.x == 0.0f) ? 1u : 0u) | ((m.y > 0.0f && t.y == 0.0f) ? 2u : 0u) |
+                             ((m.z > 0.0f && t.z == 0.0f) ? 4u : 0u) | ((m.w > 0.0f && t.w == 0.0f) ? 8u : 0u);
+        // membership word of 32 slots = the nibbles of 8 consecutive threads; a player's masks = 4 consecutive threads
+        unsigned w = (nib | (rdy << 16)) << (4 * (lane & 3));   // low half: alive nibble at its place, high half: ready nibble
+        w |= __shfl_xor_sync(FULL, w, 1);
+        w |= __shfl_xor_sync(FULL, w, 2);                        // 16 alive bits | 16 ready bits of the player, in its 4 lanes
+        unsigned mw = (w & 0xFFFFu) << (16 * ((lane >> 2) & 1));
+        mw |= __shfl_xor_sync(FULL, mw, 4);                      // membership word in the 8 lanes
+        if (valid && (lane & 7) == 0) s.sc[32 + (q >> 3)] = (int)mw;
+        if (valid && (lane & 3) == 0) {
+            s.pmask[q >> 2] = (int)(w & 0xFFFFu);
+            if (__popc(w & 0xFFFFu) >= 2) s.sc[SC_MULTI] = 1;
+            if (__popc(w >> 16) >= 2) s.sc[SC_MERGEABLE] = 1;    // the merge phase has work
         }
-        if (b) {
+        // list: warp prefix of the per-thread counts, one atomic per warp
+        const int cnt = __popc(nib);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int tot = __shfl_sync(FULL, incl, 31);
+        if (tot) {
             int pos = 0;
-            if (lane == 0) pos = atomicAdd(&s.sc[SC_NLIST], __popc(b));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (al) s.list[pos + __popc(b & ((1u << lane) - 1u))] = (uint16_t)g;
+            if (lane == 31) pos = atomicAdd(&s.sc[SC_NLIST], tot);
+            pos = __shfl_sync(FULL, pos, 31) + incl - cnt;
+            if (nib & 1u) s.list[pos++] = (uint16_t)(4 * q);
+            if (nib & 2u) s.list[pos++] = (uint16_t)(4 * q + 1);
+            if (nib & 4u) s.list[pos++] = (uint16_t)(4 * q + 2);
+            if (nib & 8u) s.list[pos++] = (uint16_t)(4 * q + 3);
         }
     }
 }
