@@ -948,11 +948,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         if (load_hash) bulk_g2s(s.hstart, ghash, hash_bytes, s.mbar);
     }
     {   // meanwhile: clear the per-tick scratch
-        for (int i = tid; i < KC / 2; i += nt) { s.cnt32[i] = 0u; reinterpret_cast<uint32_t*>(s.eater)[i] = 0xFFFFFFFFu; }
-        for (int i = tid; i < (int)gain_words(L); i += nt) s.gain[i] = 0.0f;
+        // (64-bit stores: every scratch array starts on an 8-byte boundary and holds an even number of words)
+        const uint2 ones2 = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), zero2 = make_uint2(0u, 0u);
+        for (int i = tid; i < KC / 4; i += nt) {
+            reinterpret_cast<uint2*>(s.cnt32)[i] = zero2;
+            reinterpret_cast<uint2*>(s.eater)[i] = ones2;
+        }
+        for (int i = tid; i < (int)gain_words(L) / 2; i += nt) reinterpret_cast<uint2*>(s.gain)[i] = zero2;
         if (tid < 64) s.sc[tid] = 0;
         if (a.flags & F_STEP) {
-            for (int i = tid; i < L.P_pad / 2; i += nt) reinterpret_cast<uint32_t*>(s.pwin)[i] = 0xFFFFFFFFu;
+            for (int i = tid; i < L.P_pad / 4; i += nt) reinterpret_cast<uint2*>(s.pwin)[i] = ones2;
         }
     }
     mbar_wait(s.mbar, 0);
