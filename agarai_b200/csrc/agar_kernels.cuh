@@ -1294,7 +1294,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             // scanning a quarter of the possible eaters; the lowest gid wins
             // Measured and dropped (profiles/r01i_notes.txt): culling the scan through per-bin cell counts or bin
             // heads shortens a lone CTA's critical path but not the throughput at 7 CTAs per SM.
-            auto eat_test = [&]() {
+            // With several players the same quads also make the heavy cells' virus claims (first pass only), each lane
+            // testing a quarter of the viruses.
+            auto eat_test = [&](bool claim_viruses) {
                 const int n = s.sc[SC_NLIST];
                 const int l4 = lane & 3;
                 for (int qb = (tid >> 5) * 8; qb < n; qb += nt >> 2) {  // 8 preys per warp pass, warp-uniform
@@ -1317,11 +1319,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     best = min(best, __shfl_xor_sync(FULL, best, 1));
                     best = min(best, __shfl_xor_sync(FULL, best, 2));
                     if (l4 == 0 && best != NONE_I) { s.eater[j] = (uint16_t)best; s.sc[SC_ANYEAT] = 1; }
+                    if (claim_viruses && mj >= c.virus_pop_mass) {  // lowest-gid heavy cell holding a virus centre wins it
+                        const float r2 = mj * r2pm;
+                        for (int v = l4; v < V; v += 4) {
+                            float dx = vx[v] - x, dy = vy[v] - y;
+                            if (dx * dx + dy * dy < r2) { atomicMin(&s.vwin[v], j); s.sc[SC_ANYVHIT] = 1; }
+                        }
+                    }
                 }
             };
-            // ---- apply gains (pellets, or foods when present); heavy cells claim viruses.  On a tick
-            //      without gains no mass changes here, so the eat test runs in the same phase ----
-            if (gains || V > 0) {
+            // ---- apply gains (pellets, or foods when present); in a one-player world heavy cells claim viruses here
+            //      (else the eat-test quads do).  On a tick without gains no mass changes here, so the eat test runs
+            //      in the same phase ----
+            if (gains || (V > 0 && K == 1)) {
                 const int n = s.sc[SC_NLIST];
                 const float unit = food_any ? c.food_mass : c.pellet_mass;
                 for (int q = tid; q < n; q += nt) {
@@ -1329,7 +1339,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                     float m = cm[g];
                     const int e = cnt_get(s.cnt32, g);
                     if (e) { m = m + (float)e * unit; cm[g] = m; cnt_clear(s.cnt32, g); }
-                    if (V > 0 && m >= c.virus_pop_mass) {
+                    if (V > 0 && K == 1 && m >= c.virus_pop_mass) {
                         const float r2 = m * r2pm, x = cx[g], y = cy[g];
                         for (int v = 0; v < V; ++v) {
                             float dx = vx[v] - x, dy = vy[v] - y;
@@ -1343,8 +1353,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
             PHASE(8);  // apply gains, virus claims
             // ---- cell eats cell (one code site).  It runs speculatively before the virus pops are known; a
             //      pop (rare) changes masses, voids the result and the test is taken again ----
-            for (bool again = true; again;) {
-                if (K > 1) eat_test();
+            for (bool again = true, first = true; again; first = false) {
+                if (K > 1) eat_test(first && V > 0);
                 if (gains || V > 0 || K > 1) __syncthreads();
                 again = false;
                 if (V > 0 && s.sc[SC_ANYVHIT]) {  // block-uniform, rare: out of line
