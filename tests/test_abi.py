@@ -98,3 +98,25 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
                 assert "liboracle" not in txt and "agar_oracle" not in txt.replace("oracle/agar_oracle.c", ""), f
+
+
+def test_per_config_specialised_build_exports_the_same_abi(built_lib):
+    """build.build_specialised (nvcc, cached in-tree): the per-config copy of the library exports every declared
+    symbol and computes the same layout as the default build (no GPU needed to check that)."""
+    import shutil
+    if not (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        pytest.skip("nvcc is not on this machine")
+    import ctypes as C
+    from agarai_b200 import _lib, build, config_from_gym_kwargs
+    cfg = config_from_gym_kwargs(num_envs=9, num_agents=2, num_bots=3, num_pellets=500, num_viruses=5, arena_size=200.0,
+                                 grid_size=32, observe_viruses=True, difficulty="normal")
+    path = build.build_specialised(cfg)
+    assert os.path.exists(path) and os.path.dirname(path).endswith("_jit")
+    L = _lib.load(path)
+    for name in declared_functions():
+        assert hasattr(L, name), name
+    D = _lib.load(built_lib)  # the default build
+    a, b = _lib.AgarLayout(), _lib.AgarLayout()
+    assert L.agar_layout_compute(C.byref(cfg), C.byref(a)) == 0 and D.agar_layout_compute(C.byref(cfg), C.byref(b)) == 0
+    assert bytes(a) == bytes(b)
+    assert L.agar_step_smem_bytes(C.byref(cfg)) == D.agar_step_smem_bytes(C.byref(cfg)) > 0
