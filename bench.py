@@ -84,43 +84,57 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the warm-up; the samples whose time
+    stamp falls inside the timed region (or, for a very short region, the nearest ones) are reported."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [(t, r) for t, r in self.rows if len(r) >= 10 and r[2].replace(".", "").isdigit()]
+        inside = [r for t, r in rows if self.t0 is not None and self.t0 - 0.02 <= t <= self.t1 + 0.03]
+        window = "timed region"
+        if not inside and rows and self.t0 is not None:  # region shorter than the sampling period: nearest samples
+            mid = 0.5 * (self.t0 + self.t1)
+            inside = [r for _, r in sorted(rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+            window = "nearest to the timed region"
+        sm = sorted(float(r[2]) for r in inside)
+        mx = [float(r[3]) for r in inside if r[3].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, val in zip(names, r[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
+        for r in inside:
+            for name, val in zip(names, r[6:10]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_arm(arenas, steps, warmup, nthreads, seed=0):
@@ -205,12 +219,13 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(W):
-        env.step_discrete(idx[i], out_obs=obs[i & 1])
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(W):
+        env.step_discrete(idx[i], out_obs=obs[i & 1])
     barrier()
+    sampler.mark_begin()
     l0 = env.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -218,6 +233,7 @@ def run_cuda(args):
         _, rew, done, _ = env.step_discrete(idx[W + i], out_obs=obs[i & 1])
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     launches = env.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
@@ -286,7 +302,7 @@ def run_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--arenas", type=int, default=ARENAS_PER_GPU, help="arenas per GPU")
