@@ -485,6 +485,11 @@ int agar_debug_phase_clocks(unsigned long long* h_out32) {
     CUDA_OK(cudaMemcpyToSymbol(g_phase_clocks, zero, sizeof(zero)));
     return 0;
 }
+int agar_debug_arena_cycles(unsigned int* h_out8192) {
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpyFromSymbol(h_out8192, g_arena_cycles, sizeof(unsigned int) * 8192));
+    return 0;
+}
 #endif
 
 }  // extern "C"

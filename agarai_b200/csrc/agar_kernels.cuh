@@ -26,10 +26,11 @@
 // a phase id; totals are read back with agar_debug_phase_clocks().  Compiled out of the product.
 #ifdef AGAR_PHASE_CLOCKS
 __device__ unsigned long long g_phase_clocks[32];
+__device__ unsigned int g_arena_cycles[8192];  // cycles of the last launch's CTA of each of the first 8192 arenas
 __shared__ long long ph_acc[33];  // [32] = time of the previous mark
 #define PHASE_DECL if (threadIdx.x == 0) { for (int i_ = 0; i_ < 32; ++i_) ph_acc[i_] = 0; ph_acc[32] = clock64(); }
 #define PHASE(id) do { if (threadIdx.x == 0) { const long long t_ = clock64(); ph_acc[id] += t_ - ph_acc[32]; ph_acc[32] = t_; } } while (0)
-#define PHASE_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 32; ++i_) if (ph_acc[i_]) atomicAdd(&g_phase_clocks[i_], (unsigned long long)ph_acc[i_]); } while (0)
+#define PHASE_FLUSH do { if (threadIdx.x == 0) { long long tot_ = 0; for (int i_ = 0; i_ < 32; ++i_) if (ph_acc[i_]) { atomicAdd(&g_phase_clocks[i_], (unsigned long long)ph_acc[i_]); tot_ += ph_acc[i_]; } if (arena < 8192) g_arena_cycles[arena] = (unsigned int)tot_; } } while (0)
 #else
 #define PHASE_DECL
 #define PHASE(id) do { } while (0)
