@@ -612,3 +612,17 @@ def test_per_config_specialised_library_build(oracle):
         assert np.array_equal(d.cpu().numpy(), od)
     assert np.array_equal(env.get_state().cpu().numpy().view(np.int32), oenv.get_state().view(np.int32))
     env.close()
+
+
+def test_crowded_arena_eat_test_through_bin_heads(oracle):
+    """More than 32 cells in an arena switch the cell-eats-cell test from scanning every alive cell to the per-bin
+    candidate heads + overflow list: many split cells of several players in a small arena, eats every few ticks."""
+    genv, oenv = make_pair(oracle, seed=17, num_arenas=6, num_agents=6, num_bots=6, num_viruses=2, num_pellets=300,
+                           arena_size=260.0, grid_size=16, obs_flags=7, event_capacity=4096, auto_reset=1, start_mass=300.0,
+                           split_min_mass=20.0, merge_delay=40.0, speed_k=5.0, virus_pop_mass=1e9)
+    counts = lockstep(genv, oenv, 160, np.random.default_rng(6), acts=(0, 1, 1, 2), p_act=0.7)
+    st = genv.get_state().cpu().numpy()
+    L = genv.layout
+    assert counts[4] > 20 and counts[6] > 100, counts          # cell-eaten and split events
+    assert ((st[:, L.cell_m:L.cell_m + L.cells_total] > 0).sum(1) > 32).any(), "no arena stayed crowded"
+    genv.close()
