@@ -26,8 +26,10 @@ def main():
     ap.add_argument("--policy-chunk", type=int, default=8192, help="policy forward batch (bounds activation memory)")
     ap.add_argument("--episodes", type=int, default=2)
     ap.add_argument("--amp", action="store_true", help="policy under bf16 autocast + channels_last")
+    ap.add_argument("--cudnn-benchmark", action="store_true", help="let cuDNN pick the convolution algorithms by timing")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = bool(a.cudnn_benchmark)
     W = bench.WORLDS["cfg1"]
     env = ab.BatchedAgarioEnv(ab.default_config(num_arenas=a.envs, **W), device=dev, seed=0, action_config=ab.ActionConfig(8, 1, False, False))
     need = a.envs * a.steps * env.layout.words * 4 + a.envs * 3 * 64 * 64 * 4 * 3
