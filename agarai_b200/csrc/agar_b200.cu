@@ -412,6 +412,16 @@ int agar_gae(const float* d_reward, const float* d_value, const uint8_t* d_done,
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = (tune_b == 64 || tune_b == 128) ? tune_b : 32, blocks = (N + threads - 1) / threads;
     static const int tune_nb = std::getenv("AGAR_GAE_NB") ? std::atoi(std::getenv("AGAR_GAE_NB")) : 2;
+    // Default: the TMA-fed kernel (ring of 3 shared-memory stages of 8 rows; measured 35-36 us = 61-63 % of the HBM
+    // peak at [128, 65,536] including the launch, against 38-47 us for the register-ring kernel below; 8 rows x 4
+    // stages 37 us, 16 x 2 36 us, 8 x 2 39 us).  It needs whole 128-column strips and 16-byte aligned rows.
+    static const bool no_tma = std::getenv("AGAR_GAE_NO_TMA") != nullptr;
+    auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+    if (!no_tma && (N % 128) == 0 && al16(d_reward) && al16(d_value) && al16(d_done)) {
+        agar_gae_tma_kernel<8, 3><<<N / 128, 128, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N);
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
 #define GAE_LAUNCH(U_, NB_) agar_gae_kernel<U_, NB_><<<blocks, threads, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N)
     if (tune_u == 8 && tune_nb == 2) GAE_LAUNCH(8, 2);
     else if (tune_u == 8 && tune_nb == 3) GAE_LAUNCH(8, 3);

@@ -1589,4 +1589,71 @@ __global__ void __launch_bounds__(256) agar_gae_kernel(const float* __restrict__
     }
 }
 
+// The same scan fed by TMA: a CTA owns 128 adjacent columns; one thread streams batches of U rows (512 B of r, 512 B
+// of v, 128 B of done per row, one bulk copy each) into a ring of STAGES shared-memory stages, completion counted on
+// an mbarrier per stage, while all 128 threads scan the stage that has landed.  The bytes in flight no longer live in
+// registers, so the ring can be deep (STAGES x U rows per CTA) without costing occupancy.  Needs N % 128 == 0 and
+// 16-byte aligned buffers (the host falls back to agar_gae_kernel otherwise).
+template <int U, int STAGES>
+__global__ void __launch_bounds__(128) agar_gae_tma_kernel(const float* __restrict__ r, const float* __restrict__ v,
+                                                          const uint8_t* __restrict__ done,
+                                                          const float* __restrict__ end_value, float g, float cgl,
+                                                          float* __restrict__ adv, float* __restrict__ ret, int T, int N) {
+    __shared__ __align__(16) float sr[STAGES][U][128];
+    __shared__ __align__(16) float sv[STAGES][U][128];
+    __shared__ __align__(16) uint8_t sd[STAGES][U][128];
+    __shared__ __align__(8) uint64_t full[STAGES];
+    const int tid = threadIdx.x, col0 = blockIdx.x * 128, n = col0 + tid;
+    const bool want_v = adv != nullptr, want_d = done != nullptr;
+    const int nb = (T + U - 1) / U;
+    auto issue = [&](int k) {  // batch k: rows t = T-1-k*U downwards, at most U of them, into stage k % STAGES
+        const int st = k % STAGES, t_hi = T - 1 - k * U, rows = t_hi + 1 < U ? t_hi + 1 : U;
+        mbar_expect_tx(&full[st], (uint32_t)rows * (512u + (want_v ? 512u : 0u) + (want_d ? 128u : 0u)));
+        for (int u = 0; u < rows; ++u) {
+            const size_t off = (size_t)(t_hi - u) * N + col0;
+            bulk_g2s(&sr[st][u][0], r + off, 512u, &full[st]);
+            if (want_v) bulk_g2s(&sv[st][u][0], v + off, 512u, &full[st]);
+            if (want_d) bulk_g2s(&sd[st][u][0], done + off, 128u, &full[st]);
+        }
+    };
+    if (tid == 0) {
+        for (int st = 0; st < STAGES; ++st) mbar_init(&full[st], 1);
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int k = 0; k < STAGES && k < nb; ++k) issue(k);
+    float a_next = 0.0f;
+    float g_next = end_value ? end_value[n] : 0.0f;
+    float v_next = want_v ? __ldcs(v + (size_t)T * N + n) : 0.0f;
+    for (int k = 0; k < nb; ++k) {
+        const int st = k % STAGES, t_hi = T - 1 - k * U, rows = t_hi + 1 < U ? t_hi + 1 : U;
+        mbar_wait(&full[st], (uint32_t)((k / STAGES) & 1));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (u >= rows) break;
+            const int t = t_hi - u;
+            const size_t i = (size_t)t * N + n;
+            const float rr = sr[st][u][tid];
+            const bool cut = want_d && sd[st][u][tid] != 0;
+            if (adv) {
+                const float vv = sv[st][u][tid];
+                float vn = cut ? 0.0f : v_next;
+                float delta = (rr + g * vn) - vv;
+                float av = (t == T - 1 || cut) ? delta : delta + cgl * a_next;
+                __stcs(adv + i, av);
+                a_next = av;
+                v_next = vv;
+            }
+            if (ret) {
+                float gn = cut ? 0.0f : g_next;
+                float G_t = rr + g * gn;
+                __stcs(ret + i, G_t);
+                g_next = G_t;
+            }
+        }
+        __syncthreads();  // every thread has read stage st: it can be refilled
+        if (tid == 0 && k + STAGES < nb) issue(k + STAGES);
+    }
+}
+
 }  // namespace agar

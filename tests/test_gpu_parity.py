@@ -249,7 +249,10 @@ def test_gae_matches_oracle_and_reference_golden(oracle):
         assert np.array_equal(adv.cpu().numpy()[:, 0], z["adv"][:, n])
         assert np.array_equal(ret.cpu().numpy()[:, 0], z["ret0"][:, n])
     rng = np.random.default_rng(8)
-    for T, N in ((1, 1), (3, 5), (128, 1000), (513, 257), (7, 4099)):
+    # N % 128 == 0 takes the TMA-fed kernel (ring of 8-row stages: T below, at and across the stage and ring sizes);
+    # other widths the register-ring kernel
+    for T, N in ((1, 1), (3, 5), (128, 1000), (513, 257), (7, 4099), (1, 128), (8, 256), (9, 128), (24, 384), (25, 128),
+                 (128, 65536), (131, 1280)):
         rr = rng.normal(size=(T, N)).astype(f32); vv = rng.normal(size=(T + 1, N)).astype(f32)
         dd = (rng.random((T, N)) < 0.05).astype(np.uint8); ev = rng.normal(size=N).astype(f32)
         for done, end in ((None, None), (dd, ev)):
@@ -259,6 +262,8 @@ def test_gae_matches_oracle_and_reference_golden(oracle):
             oadv, oret = oracle.gae(rr, vv, 0.75, 0.1, done=done, end_value=end)
             assert np.array_equal(adv.cpu().numpy().view(np.int32), oadv.view(np.int32)), (T, N)
             assert np.array_equal(ret.cpu().numpy().view(np.int32), oret.view(np.int32)), (T, N)
+        only_ret = ab.make_returns(torch.from_numpy(rr).cuda(), 0.75, end_value=torch.from_numpy(ev).cuda())  # no value buffer
+        assert np.array_equal(only_ret.cpu().numpy().view(np.int32), oracle.gae(rr, vv, 0.75, 0.0, end_value=ev, want_adv=False)[1].view(np.int32)), (T, N)
     # rl/test.py:59-81 known answers through the CUDA path
     r3 = torch.tensor([[0.0], [3.0], [0.0]], device="cuda")
     for gamma in (1.0, 0.5, 0.0):

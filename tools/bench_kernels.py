@@ -50,7 +50,7 @@ def main():
     d = (torch.rand(T, N, device=dev) < 0.01).to(torch.uint8)
     ev = v[T].clone()
     ms = timed(lambda: ab.gae_and_returns(r, v, 0.75, 0.1, dones=d, end_value=ev), a.reps, flush)
-    report("agar_gae_kernel", ms, T * N * 17 + N * 8, {"T": T, "N": N})
+    report("agar_gae_tma_kernel", ms, T * N * 17 + N * 8, {"T": T, "N": N})
     if a.only == "gae":
         return
 
