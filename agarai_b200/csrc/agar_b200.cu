@@ -72,6 +72,7 @@ struct AgarEnv {
     int32_t n_actions = 0;
     size_t smem = 0;
     int min_blocks = 5;  // which agar_step_kernel instantiation to launch
+    int threads = kThreads;  // threads per arena (CTA size) of that instantiation
     StepKernel kernel = nullptr;
     const char* kernel_name = "";
     int64_t launches = 0;
@@ -80,6 +81,12 @@ struct AgarEnv {
     float* d_reward = nullptr; uint8_t* d_done = nullptr;
     cudaStream_t host_stream = nullptr, host_stream2 = nullptr;
     cudaEvent_t host_event = nullptr;
+    // ordering of agar_step_host (private streams) against work the caller enqueued on its own streams
+    cudaEvent_t order_event = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool pending = false;        // work was enqueued on last_stream since the last agar_step_host
+    bool pending_multi = false;  // ... on more than one caller stream
+    bool persist_hash = true;    // AGAR_NO_PERSIST (debug switch) read once at create
 };
 
 namespace {
@@ -89,11 +96,19 @@ size_t obs_elems(const AgarEnv* e) {
     return (size_t)c.num_arenas * c.num_agents * e->p.C * c.grid_size * c.grid_size;
 }
 
-int launch(AgarEnv* e, KArgs& a, int n_records, cudaStream_t st) {
+// remembers on which caller stream work is in flight (see agar_step_host)
+void note_stream(AgarEnv* e, cudaStream_t st) {
+    if (e->pending && st != e->last_stream) e->pending_multi = true;
+    e->last_stream = st;
+    e->pending = true;
+}
+
+int launch(AgarEnv* e, KArgs& a, int n_records, cudaStream_t st, bool caller_stream = true) {
     a.n_records = n_records;
-    e->kernel<<<n_records, kThreads, e->smem, st>>>(e->p, a);
+    e->kernel<<<n_records, e->threads, e->smem, st>>>(e->p, a);
     CUDA_OK(cudaGetLastError());
     e->launches += 1;
+    if (caller_stream) note_stream(e, st);
     return 0;
 }
 
@@ -104,7 +119,7 @@ KArgs base_args(AgarEnv* e) {
     a.src_state = e->d_state;
     a.events = e->d_events;
     a.ev_counts = e->d_ev_counts;
-    a.hash = std::getenv("AGAR_NO_PERSIST") ? nullptr : e->d_hash;  // debug switch: rebuild the pellet hash every step
+    a.hash = e->persist_hash ? e->d_hash : nullptr;  // (AGAR_NO_PERSIST: rebuild the pellet hash every step)
     return a;
 }
 
@@ -130,20 +145,11 @@ int agar_layout_compute(const AgarConfig* cfg, AgarLayout* out) {
 
 int agar_obs_channels(const AgarConfig* cfg) { return cfg ? agar_spec_obs_channels(cfg) : 0; }
 
-int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
-    if (!cfg || !out) return fail("NULL argument");
-    if (const char* m = agar_spec_config_check(cfg)) return fail(std::string("bad config: ") + m);
-    int ndev = 0;
-    CUDA_OK(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) return fail("no such CUDA device");
-    CUDA_OK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return fail("libagar_b200 is built for sm_100a (B200) only");
+int agar_destroy(AgarEnv* e);
 
-    AgarEnv* e = new (std::nothrow) AgarEnv();
-    if (!e) return fail("out of host memory");
+static int create_impl(const AgarConfig* cfg, int device, AgarEnv* e, const cudaDeviceProp& prop) {
     e->device = device;
+    e->persist_hash = std::getenv("AGAR_NO_PERSIST") == nullptr;
     DevParams& p = e->p;
     std::memset(&p, 0, sizeof(p));
     p.c = *cfg;
@@ -164,7 +170,6 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
     for (int i = 0; i < G; ++i) p.oob_off[i] = (float)((double)(i - G / 2) * box_d);
     e->smem = smem_bytes(p.L, G);
     if (e->smem > (size_t)prop.sharedMemPerBlockOptin) {
-        delete e;
         return fail("arena record + observation tile do not fit in shared memory (" + std::to_string(e->smem) + " B)");
     }
     // CTAs per SM that the shared memory allows (1 KB per CTA is reserved by the system)
@@ -179,7 +184,12 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
     // a per-config copy of the library (build.build_specialised) carries only its own specialisation
     if (!generic_only && matches<CvExtra>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, AGAR_EXTRA_CV_BLOCKS, CvExtra>; e->kernel_name = "extra"; }
 #else
-    if (!generic_only && matches<CvCfg2>(*cfg, p.L)) { e->kernel = agar_step_kernel<kThreads, 7, CvCfg2>; e->kernel_name = "cfg2"; }
+    if (!generic_only && matches<CvCfg2>(*cfg, p.L)) {
+        e->kernel = agar_step_kernel<kThreads, 7, CvCfg2>; e->kernel_name = "cfg2";
+        if (const char* th = std::getenv("AGAR_THREADS")) {  // tuning switch: threads per arena
+            if (std::atoi(th) == 64) { e->kernel = agar_step_kernel<64, 7, CvCfg2>; e->threads = 64; }
+        }
+    }
     else if (!generic_only && matches<CvCfg1>(*cfg, p.L)) {
         e->kernel_name = "cfg1";
         const char* mb = std::getenv("AGAR_MIN_BLOCKS");
@@ -203,19 +213,42 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
     CUDA_OK(cudaFuncSetAttribute(e->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     const size_t state_bytes = (size_t)cfg->num_arenas * p.L.words * sizeof(float);
     CUDA_OK(cudaMalloc(&e->d_state, state_bytes));
-    CUDA_OK(cudaMemset(e->d_state, 0, state_bytes));
+    CUDA_OK(cudaMemsetAsync(e->d_state, 0, state_bytes, 0));
     p.hash_words = (int)hash_record_words(p.L);
     p.hash_epoch = 1;
     CUDA_OK(cudaMalloc(&e->d_hash, (size_t)cfg->num_arenas * p.hash_words * sizeof(int32_t)));
-    CUDA_OK(cudaMemset(e->d_hash, 0, (size_t)cfg->num_arenas * p.hash_words * sizeof(int32_t)));  // epoch 0 = stale
+    CUDA_OK(cudaMemsetAsync(e->d_hash, 0, (size_t)cfg->num_arenas * p.hash_words * sizeof(int32_t), 0));  // epoch 0 = stale
     if (cfg->event_capacity > 0) {
         CUDA_OK(cudaMalloc(&e->d_events, (size_t)cfg->num_arenas * cfg->event_capacity * 4 * sizeof(int32_t)));
         CUDA_OK(cudaMalloc(&e->d_ev_counts, (size_t)cfg->num_arenas * sizeof(int32_t)));
-        CUDA_OK(cudaMemset(e->d_ev_counts, 0, (size_t)cfg->num_arenas * sizeof(int32_t)));
+        CUDA_OK(cudaMemsetAsync(e->d_ev_counts, 0, (size_t)cfg->num_arenas * sizeof(int32_t), 0));
+    }
+    CUDA_OK(cudaEventCreateWithFlags(&e->order_event, cudaEventDisableTiming));
+    // the clears ran on the legacy stream, which non-blocking caller streams do not wait for: finish them here
+    CUDA_OK(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
+    if (!cfg || !out) return fail("NULL argument");
+    if (const char* m = agar_spec_config_check(cfg)) return fail(std::string("bad config: ") + m);
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail("no such CUDA device");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("libagar_b200 is built for sm_100a (B200) only");
+    AgarEnv* e = new (std::nothrow) AgarEnv();
+    if (!e) return fail("out of host memory");
+    if (int rc = create_impl(cfg, device, e, prop)) {  // g_err is set; release whatever was allocated
+        agar_destroy(e);
+        return rc;
     }
     *out = e;
     return 0;
 }
+
 
 int agar_destroy(AgarEnv* e) {
     if (!e) return 0;
@@ -226,6 +259,7 @@ int agar_destroy(AgarEnv* e) {
     if (e->host_stream) cudaStreamDestroy(e->host_stream);
     if (e->host_stream2) cudaStreamDestroy(e->host_stream2);
     if (e->host_event) cudaEventDestroy(e->host_event);
+    if (e->order_event) cudaEventDestroy(e->order_event);
     delete e;
     return 0;
 }
@@ -245,20 +279,23 @@ int agar_get_layout(const AgarEnv* e, AgarLayout* out) {
 int agar_seed(AgarEnv* e, uint64_t seed) {
     if (!e) return fail("env is NULL");
     CUDA_OK(cudaSetDevice(e->device));
+    // no stream argument: the call is synchronous with respect to everything in flight on the device (steps the
+    // caller enqueued on non-blocking streams included), before and after the tick counters are cleared
+    CUDA_OK(cudaDeviceSynchronize());
     e->p.seed_lo = (uint32_t)seed;
     e->p.seed_hi = (uint32_t)(seed >> 32);
     e->p.hash_epoch += 1;  // conservative: persisted hashes are rebuilt
     // tick counters restart from 0: one strided 4-byte memset per arena record
-    CUDA_OK(cudaMemset2D(e->d_state + e->p.L.tick, (size_t)e->p.L.words * sizeof(float), 0, sizeof(int32_t),
-                         (size_t)e->p.c.num_arenas));
+    CUDA_OK(cudaMemset2DAsync(e->d_state + e->p.L.tick, (size_t)e->p.L.words * sizeof(float), 0, sizeof(int32_t),
+                              (size_t)e->p.c.num_arenas, 0));
+    CUDA_OK(cudaStreamSynchronize(0));
     return 0;
 }
 
 int agar_reset(AgarEnv* e, const uint8_t* d_reset_mask, float* d_obs, void* stream) {
     if (!e) return fail("env is NULL");
     CUDA_OK(cudaSetDevice(e->device));
-    e->p.hash_epoch += 1;  // pellets are redrawn: persisted hashes are stale
-    KArgs a = base_args(e);
+    KArgs a = base_args(e);  // the kernel marks the persisted pellet hash of every arena it resets as stale
     a.flags = F_RESET | (d_obs ? F_OBS : 0);
     a.reset_mask = d_reset_mask;
     a.obs = d_obs;
@@ -329,6 +366,7 @@ int agar_get_state(AgarEnv* e, float* d_dst, void* stream) {
     CUDA_OK(cudaSetDevice(e->device));
     CUDA_OK(cudaMemcpyAsync(d_dst, e->d_state, (size_t)e->p.c.num_arenas * e->p.L.words * sizeof(float),
                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    note_stream(e, (cudaStream_t)stream);
     return 0;
 }
 
@@ -338,6 +376,7 @@ int agar_set_state(AgarEnv* e, const float* d_src, void* stream) {
     CUDA_OK(cudaMemcpyAsync(e->d_state, d_src, (size_t)e->p.c.num_arenas * e->p.L.words * sizeof(float),
                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     e->p.hash_epoch += 1;  // the pellets may have changed: every persisted hash is stale
+    note_stream(e, (cudaStream_t)stream);
     return 0;
 }
 
@@ -349,6 +388,7 @@ int agar_events(AgarEnv* e, int32_t* d_events, int32_t* d_counts, void* stream) 
     const size_t N = (size_t)e->p.c.num_arenas;
     CUDA_OK(cudaMemcpyAsync(d_events, e->d_events, N * cap * 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     CUDA_OK(cudaMemcpyAsync(d_counts, e->d_ev_counts, N * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    note_stream(e, (cudaStream_t)stream);
     return 0;
 }
 
@@ -358,16 +398,38 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
     if (!h_target_xy || !h_act || !h_reward || !h_done) return fail("agar_step_host: NULL buffer");
     CUDA_OK(cudaSetDevice(e->device));
     const size_t N = (size_t)e->p.c.num_arenas, A = (size_t)e->p.c.num_agents, NA = N * A;
-    if (!e->host_stream) {
-        CUDA_OK(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
-        CUDA_OK(cudaStreamCreateWithFlags(&e->host_stream2, cudaStreamNonBlocking));
-        CUDA_OK(cudaEventCreateWithFlags(&e->host_event, cudaEventDisableTiming));
-        CUDA_OK(cudaMalloc(&e->d_target, NA * 2 * sizeof(float)));
-        CUDA_OK(cudaMalloc(&e->d_act, NA * sizeof(int32_t)));
-        CUDA_OK(cudaMalloc(&e->d_reward, NA * sizeof(float)));
-        CUDA_OK(cudaMalloc(&e->d_done, NA));
+    if (!e->host_stream) {  // first call: private streams and staging buffers; the handle keeps them only if all succeed
+        cudaStream_t s1 = nullptr, s2 = nullptr;
+        cudaEvent_t ev = nullptr;
+        float* t = nullptr; int32_t* ac = nullptr; float* rw = nullptr; uint8_t* dn = nullptr;
+        cudaError_t err = cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking);
+        if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaMalloc(&t, NA * 2 * sizeof(float));
+        if (err == cudaSuccess) err = cudaMalloc(&ac, NA * sizeof(int32_t));
+        if (err == cudaSuccess) err = cudaMalloc(&rw, NA * sizeof(float));
+        if (err == cudaSuccess) err = cudaMalloc(&dn, NA);
+        if (err != cudaSuccess) {
+            if (s1) cudaStreamDestroy(s1);
+            if (s2) cudaStreamDestroy(s2);
+            if (ev) cudaEventDestroy(ev);
+            cudaFree(t); cudaFree(ac); cudaFree(rw); cudaFree(dn);
+            return fail(std::string("agar_step_host: staging allocation failed: ") + cudaGetErrorString(err));
+        }
+        e->host_stream = s1; e->host_stream2 = s2; e->host_event = ev;
+        e->d_target = t; e->d_act = ac; e->d_reward = rw; e->d_done = dn;
     }
     if (h_obs && !e->d_obs) CUDA_OK(cudaMalloc(&e->d_obs, obs_elems(e) * sizeof(float)));
+    // The private streams are non-blocking: order them after whatever the caller enqueued on its own stream(s)
+    // (agar_reset, agar_step, agar_set_state ...) since the previous host-buffer step.
+    if (e->pending) {
+        if (e->pending_multi) CUDA_OK(cudaDeviceSynchronize());
+        else {
+            CUDA_OK(cudaEventRecord(e->order_event, e->last_stream));
+            CUDA_OK(cudaStreamWaitEvent(e->host_stream, e->order_event, 0));
+        }
+        e->pending = false; e->pending_multi = false;
+    }
     cudaStream_t st = e->host_stream, st2 = e->host_stream2;
     CUDA_OK(cudaMemcpyAsync(e->d_target, h_target_xy, NA * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(e->d_act, h_act, NA * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -382,7 +444,7 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
         a.target_xy = e->d_target; a.act = e->d_act; a.obs = h_obs ? e->d_obs : nullptr;
         a.reward = e->d_reward; a.done = e->d_done;
         a.arena0 = a0;
-        if (int rc = launch(e, a, a1 - a0, st)) return rc;
+        if (int rc = launch(e, a, a1 - a0, st, false)) return rc;
         if (h_obs) {
             CUDA_OK(cudaEventRecord(e->host_event, st));
             CUDA_OK(cudaStreamWaitEvent(st2, e->host_event, 0));
@@ -460,6 +522,7 @@ int agar_observe_ram(AgarEnv* e, int32_t n_pellet, int32_t n_virus, int32_t n_fo
     ram_features_kernel<<<c.num_arenas * c.num_agents, 128, smem, (cudaStream_t)stream>>>(e->p, rp, e->d_state, d_out);
     CUDA_OK(cudaGetLastError());
     e->launches += 1;
+    note_stream(e, (cudaStream_t)stream);
     return 0;
 }
 

@@ -971,14 +971,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     bool static_dirty = false;  // whole record must be written back (after a reset)
     int persist_hash = 0;       // 0: the persisted hash is current, 1: its slot order changed, 2: rebuilt
     if (a.flags & F_RESET) {
-        if (!a.reset_mask || a.reset_mask[arena]) { reset_arena<CV>(p, gid_lo, gid_hi); static_dirty = true; }
+        if (!a.reset_mask || a.reset_mask[arena]) {
+            reset_arena<CV>(p, gid_lo, gid_hi); static_dirty = true;
+            // the pellets of this arena (only) were redrawn: its persisted hash is stale
+            if (tid == 0 && a.hash && !(a.flags & F_READONLY))
+                *reinterpret_cast<int4*>(a.hash + (size_t)arena * hash_words + hash_body_words(L)) = make_int4(0, 0, 0, 0);
+        }
     }
 
     if (a.flags & F_STEP) {
         const uint32_t tick0 = (uint32_t)s.reci[L.tick];
         PHASE(0);  // staging
         // ---- pellet hash (persisted across steps, rebuilt when stale), alive list ----
-        if (load_hash && hhdr.x == p.hash_epoch) {
+        if (load_hash && hhdr.x == p.hash_epoch && !static_dirty) {
             if (tid == 0) s.sc[SC_HASHOK] = 1;
         } else {
             build_hash<CV>(p);

@@ -214,6 +214,12 @@ def run_cuda(args):
     idx = torch.randint(0, env.num_actions, (K + W, N, A), generator=gen, device=dev, dtype=torch.int32)
     obs = [torch.empty(env.obs_shape, dtype=torch.float32, device=dev) for _ in range(2)]
     env.reset(out_obs=obs[0])
+    if args.age > 0:  # fast-forward every arena to a fixed episode age with the same random policy (untimed)
+        ga = torch.Generator(device=dev); ga.manual_seed(args.seed + 1000 + rank)
+        for t in range(args.age):
+            ia = torch.randint(0, env.num_actions, (N, A), generator=ga, device=dev, dtype=torch.int32)
+            env.step_discrete(ia, out_obs=obs[t & 1], want_obs=not args.no_obs)
+        torch.cuda.synchronize(dev)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -225,14 +231,14 @@ def run_cuda(args):
     if rank == 0:
         sampler.start()
     for i in range(W):
-        env.step_discrete(idx[i], out_obs=obs[i & 1])
+        env.step_discrete(idx[i], out_obs=obs[i & 1], want_obs=not args.no_obs)
     barrier()
     sampler.mark_begin()
     l0 = env.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        _, rew, done, _ = env.step_discrete(idx[W + i], out_obs=obs[i & 1])
+        _, rew, done, _ = env.step_discrete(idx[W + i], out_obs=obs[i & 1], want_obs=not args.no_obs)
     e1.record()
     barrier()
     sampler.mark_end()
@@ -311,6 +317,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--age", type=int, default=0, help="untimed steps run before the warm-up (episode age of the timed region)")
+    ap.add_argument("--no-obs", action="store_true", help="tuning only: step without the observation raster")
     ap.add_argument("--world", default="cfg2", choices=sorted(WORLDS), help="BASELINE.json world (default: the headline cfg2)")
     ap.add_argument("--set", action="append", default=[], metavar="FIELD=VALUE",
                     help="tuning experiments only: override a world field (e.g. ticks_per_step=8); the line says so in config")

@@ -13,11 +13,18 @@ from agarai_b200 import _lib
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 W = dict(bench.WORLDS[sys.argv[2] if len(sys.argv) > 2 else "cfg2"])
+AGE = 0
 for kv in sys.argv[3:]:
-    k, v = kv.split("="); W[k] = type(W[k])(float(v))
+    k, v = kv.split("=")
+    if k == "AGE":
+        AGE = int(v); continue
+    W[k] = type(W[k])(float(v))
 env = ab.BatchedAgarioEnv(ab.default_config(num_arenas=n, **W), device="cuda:0", seed=0, action_config=ab.ActionConfig(8, 1, True, True))
 obs = env.reset()
 idx = torch.randint(0, env.num_actions, (120, n, W["num_agents"]), device="cuda", dtype=torch.int32)
+g = torch.Generator(device="cuda"); g.manual_seed(1)
+for t in range(AGE):
+    env.step_discrete(torch.randint(0, env.num_actions, (n, W["num_agents"]), generator=g, device="cuda", dtype=torch.int32), out_obs=obs)
 for i in range(20):
     env.step_discrete(idx[i], out_obs=obs)
 L = _lib.lib()
