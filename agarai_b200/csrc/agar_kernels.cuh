@@ -196,6 +196,7 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------- half-warp (one player) helpers
 // A player's 16 cell slots map to the 16 lanes of a half-warp: hbase is 0 or 16, slot = lane & 15.
@@ -1493,7 +1494,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         const int w0 = static_dirty ? 0 : L.dyn_begin;  // dyn_begin % 4 == 0
         __syncthreads();                 // every thread's writes to the record are done
         if (tid == 0) {
-            fence_async_all();           // ... and ordered before the async proxy (shared and global)
+            // ... and ordered before the async proxy's reads of shared memory (the narrow fence: the full one also
+            // waits for this thread's global stores).  After a reset the bulk store covers the pellet / virus words
+            // that respawns wrote to global memory with plain stores earlier in this step: only then must the global
+            // side be ordered too.
+            if (static_dirty) fence_async_all(); else fence_async_smem();
             bulk_s2g(grec + w0, s.rec + w0, (uint32_t)(L.words - w0) * 4u);
             if (persist_hash) {          // [hstart | sorted] or only the slots; the raster below only reads them
                 const int h0 = persist_hash == 2 ? 0 : HASH_BINS + 4;

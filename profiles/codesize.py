@@ -8,7 +8,7 @@ bucket = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 cur = None; infn = False; counts = collections.Counter(); inl = collections.Counter()
 for l in txt:
     if l.startswith(".text."):
-        infn = "agar_step_kernelILi128ELi6" in l
+        infn = "agar_step_kernelILi128ELi7ENS_5StCfgILi1ELi25" in l
     if not infn: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', l)
     if m:
