@@ -10,14 +10,21 @@ action set with split and feed.  One "step" = one env.step of every arena on eve
 kernel launch per GPU.  Arenas never interact, so N GPUs = N independent shards (weak scaling,
 no collective on the data path); RNG is keyed by global arena id.
 
-`value`   device-resident: action indices already in HBM, observations written to HBM.  The steps follow a reset,
-          and an arena-step gets dearer as episodes age (cells grow, viruses pop them into many pieces): the default
-          200 steps give ~30 M env-steps/s on one B200, `--steps 2000` ~18.5 M.
+Episode age.  An arena-step gets dearer as episodes age (cells grow, viruses pop them into many pieces), and a
+training run lives in the steady state, not in the first steps after a reset.  Both arms therefore fast-forward
+every arena by `--age` untimed steps of the same random policy (default 1000: the alive-cell and mass
+distributions are stationary from ~1000 steps on, profiles/r02_notes.txt) before the warm-up;
+`config.episode_age_steps` says so, and the line also carries the post-reset figure as `young_world`.
+
+`value`   device-resident: action indices already in HBM, observations written to HBM.
 `e2e`     the same step through agar_step_host: actions from pinned host memory, observations,
           rewards and dones copied back to pinned host memory inside the timed region.
 `roofline` algorithmic bytes per env-step x arenas per launch / launch duration.
+`extras`  the other BASELINE configs on the same box and in the same run: cfg1-world and cfg4-world steps
+          (configs[0]/[2]/[4] and configs[3]; cfg4 at 32,768 arenas per GPU = 262,144 arenas on 8 GPUs), `agar_gae` at
+          [128, 65,536] (configs[2]) and the observe-only raster, each with its launch time and fraction of the HBM peak.
 `cpu_baseline` the CPU oracle (a port: the reference's simulator is an absent external package)
-          on this box's host cores, on a bounded sample of the same workload.
+          on this box's host cores, on a bounded sample of the same workload at the same episode age.
 """
 import argparse
 import json
@@ -32,6 +39,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ARENAS_PER_GPU = 4096
+DEFAULT_AGE = 1000
 WORLDS = {
     # BASELINE.json configs[1] (the headline): viruses + bot opponents (a2c/train.py:19-27 values)
     "cfg2": dict(num_agents=1, num_bots=25, num_viruses=25, num_pellets=1000, arena_size=500.0, ticks_per_step=4,
@@ -53,6 +61,7 @@ WORLDS = {
 WORLD = WORLDS["cfg2"]
 METRIC = "env_steps_per_sec_incl_grid_obs"
 UNIT = "env-steps/s"
+CFG4_ARENAS_PER_GPU = 32768  # BASELINE configs[3]: 262,144 arenas over 8 GPUs
 
 
 def algorithmic_bytes_per_env_step(w=None):
@@ -85,9 +94,15 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def describe(w):
+    return (f"{w['num_agents']} agent(s) + {w['num_bots']} bots + {w['num_viruses']} viruses, {w['num_pellets']} pellets, "
+            f"arena {w['arena_size']:g}, obs {bin(w['obs_flags']).count('1')}x{w['grid_size']}x{w['grid_size']} f32 per agent")
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the warm-up; the samples whose time
-    stamp falls inside the timed region (or, for a very short region, the nearest ones) are reported."""
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms for the whole run.  A region is reported from the
+    samples whose time stamp falls inside it; the caller makes every region at least ~100 ms of the same load (the
+    untimed ageing / repeat steps count: same kernel, same arenas), so a region is never empty."""
 
     Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -95,13 +110,15 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
-        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t_end = time.time() + 5.0  # nvidia-smi needs a moment before its first line
+            while not self.rows and time.time() < t_end:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
@@ -109,24 +126,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def mark_begin(self):
-        self.t0 = time.time()
-
-    def mark_end(self):
-        self.t1 = time.time()
-
-    def stop(self):
+    def region(self, t0, t1):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
-        self.proc.terminate()
-        rows = [(t, r) for t, r in self.rows if len(r) >= 10 and r[2].replace(".", "").isdigit()]
-        inside = [r for t, r in rows if self.t0 is not None and self.t0 - 0.02 <= t <= self.t1 + 0.03]
-        window = "timed region"
-        if not inside and rows and self.t0 is not None:  # region shorter than the sampling period: nearest samples
-            mid = 0.5 * (self.t0 + self.t1)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        rows = [(t, r) for t, r in list(self.rows) if len(r) >= 10 and r[2].replace(".", "").isdigit()]
+        inside = [r for t, r in rows if t0 - 0.01 <= t <= t1 + 0.01]
+        window = "region under load"
+        if not inside and rows:
+            mid = 0.5 * (t0 + t1)
             inside = [r for _, r in sorted(rows, key=lambda tr: abs(tr[0] - mid))[:3]]
-            window = "nearest to the timed region"
+            window = "nearest samples"
         sm = sorted(float(r[2]) for r in inside)
         mx = [float(r[3]) for r in inside if r[3].replace(".", "").isdigit()]
         reasons = set()
@@ -138,9 +147,14 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
 
-def cpu_arm(arenas, steps, warmup, nthreads, seed=0):
-    """Times the CPU oracle (oracle/agar_oracle.c) on `arenas` arenas of the bench world."""
+
+def cpu_arm(arenas, steps, warmup, nthreads, age=0, seed=0):
+    """Times the CPU oracle (oracle/agar_oracle.c) on `arenas` arenas of the bench world, aged by `age` untimed steps
+    of the same random policy.  Returns (env-steps/s, seconds per step, seconds spent ageing)."""
     import numpy as np
     from oracle import oracle as O
     import agarai_b200.actions as act_mod
@@ -149,107 +163,237 @@ def cpu_arm(arenas, steps, warmup, nthreads, seed=0):
     obs = env.reset()
     xy_tab, act_tab = act_mod.ppo_action_table(act_mod.ActionConfig(8, 1, True, True))
     rng = np.random.default_rng(seed)
+    A = WORLD["num_agents"]
+    t_age = time.perf_counter()
+    for _ in range(age):
+        idx = rng.integers(0, len(act_tab), size=(arenas, A))
+        env.step(xy_tab[idx], act_tab[idx], want_obs=False)
+    t_age = time.perf_counter() - t_age
     times = []
     for i in range(warmup + steps):
-        idx = rng.integers(0, len(act_tab), size=(arenas, WORLD["num_agents"]))
+        idx = rng.integers(0, len(act_tab), size=(arenas, A))
         t0 = time.perf_counter()
         env.step(xy_tab[idx], act_tab[idx], out=obs)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     env.close()
-    return arenas * len(times) / sum(times), sum(times) / len(times)
+    return arenas * len(times) / sum(times), sum(times) / len(times), t_age
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path on the host cores.  The reference's own
-    simulator (gym_agario) is an external package that is not available, so this arm runs the
-    oracle port, multi-threaded over arenas (kind = "port")."""
+    """--impl reference: the CPU implementation of the path on the host cores, on the arm's own config: all
+    4096 arenas, aged by the same number of untimed steps.  The reference's own simulator (gym_agario) is an
+    external package that is not available, so this arm runs the oracle port, multi-threaded over arenas
+    (kind = "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 512
-    value, sec = cpu_arm(sample, args.steps, args.warmup, cores)
+    N = args.arenas
+    value, sec, t_age = cpu_arm(N, args.steps, args.warmup, cores, age=args.age)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.world}: {WORLD['num_agents']} agent(s) + {WORLD['num_bots']} bots + "
-                               f"{WORLD['num_viruses']} viruses, {WORLD['num_pellets']} pellets, arena "
-                               f"{WORLD['arena_size']:g}, obs {bin(WORLD['obs_flags']).count('1')}x{WORLD['grid_size']}x{WORLD['grid_size']} f32 per agent",
-                   "arenas_per_step": sample, **WORLD},
+        "config": {"workload": f"{args.world}: {N} arenas, {describe(WORLD)}, random policy over 25 actions (8 dirs, split, feed)",
+                   "arenas_per_step": N, "episode_age_steps": args.age, **WORLD},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} arenas x {args.steps} steps (of the {ARENAS_PER_GPU}-arena workload), "
+                         "sample": f"all {N} arenas x {args.steps} steps after {args.age} untimed ageing steps ({t_age:.0f} s), "
                                    "oracle/agar_oracle.c with one pthread per core"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+class _Ctx:
+    """Per-process CUDA / distributed context of the CUDA arm."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback; use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def timed(self, fn, reps):
+        """device time of `reps` calls of fn(i) between two barriers, max over ranks; returns (ms, wall t0, wall t1)"""
+        from agarai_b200 import sharding
+        torch = self.torch
+        self.barrier()
+        t0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        self.barrier()
+        return sharding.max_over_ranks(e0.elapsed_time(e1), self.dev), t0, time.time()
+
+
+def time_world(ctx, world_name, arenas, steps, warmup, age, seed, no_obs=False, want_young=False):
+    """Steps one BASELINE world device-resident.  Returns a dict with ms per launch (max over ranks), env-steps/s of the
+    whole job, the roofline fraction and the wall-clock window of the loaded region (for the clock sampler)."""
+    import agarai_b200 as ab
+    from agarai_b200 import sharding
+    torch = ctx.torch
+    w = WORLD if world_name is None else WORLDS[world_name]
+    A = w["num_agents"]
+    ac = ab.ActionConfig(8, 1, True, True)
+    shard = sharding.shard_from_env(arenas)  # rank r owns global arenas [r*N, (r+1)*N): no data-path collective
+    cfg = ab.default_config(num_arenas=arenas, arena_id_base=shard.arena_id_base, **w)
+    env = ab.BatchedAgarioEnv(cfg, device=ctx.dev, seed=seed, action_config=ac)
+    gen = torch.Generator(device=ctx.dev); gen.manual_seed(seed + ctx.rank)
+    idx = torch.randint(0, env.num_actions, (steps + warmup, arenas, A), generator=gen, device=ctx.dev, dtype=torch.int32)
+    obs = [torch.empty(env.obs_shape, dtype=torch.float32, device=ctx.dev) for _ in range(2)]
+    env.reset(out_obs=obs[0])
+    out = {"env": env, "idx": idx, "obs": obs}
+
+    def step(i, base=0):
+        env.step_discrete(idx[base + i], out_obs=obs[i & 1], want_obs=not no_obs)
+
+    if want_young:  # the post-reset regime (what round 1 reported), before the ageing below
+        for i in range(warmup):
+            step(i)
+        ms, _, _ = ctx.timed(lambda i: step(i, warmup), steps)
+        out["young_ms_per_launch"] = ms / steps
+    t_load0 = time.time()
+    if age > 0:  # fast-forward every arena with the same random policy (untimed)
+        ga = torch.Generator(device=ctx.dev); ga.manual_seed(seed + 1000 + ctx.rank)
+        for t in range(age):
+            ia = torch.randint(0, env.num_actions, (arenas, A), generator=ga, device=ctx.dev, dtype=torch.int32)
+            env.step_discrete(ia, out_obs=obs[t & 1], want_obs=not no_obs)
+    for i in range(warmup):
+        step(i)
+    l0 = env.launch_count
+    ms, _, t1 = ctx.timed(lambda i: step(i, warmup), steps)
+    out["launches"] = env.launch_count - l0
+    # keep the same load running until the region holds a handful of clock samples (untimed)
+    while time.time() - t_load0 < 0.15:
+        for i in range(min(steps, 20)):
+            step(i, warmup)
+        torch.cuda.synchronize(ctx.dev)
+        t1 = time.time()
+    out.update(ms_per_launch=ms / steps, window=(t_load0, t1), world=w, arenas=arenas, steps=steps)
+    return out
+
+
+def roofline_of(w, arenas, ms_per_launch, peak):
+    B = algorithmic_bytes_per_env_step(w)
+    gbs = B * arenas / (ms_per_launch * 1e-3) / 1e9
+    return B, gbs, gbs / peak
+
+
+def run_extras(ctx, args, sampler, peak):
+    """The other BASELINE configs, each timed like the headline (CUDA events, max over ranks)."""
+    import agarai_b200 as ab
+    torch = ctx.torch
+    extras = {}
+    K, W = max(args.steps, 10), max(args.warmup, 3)
+
+    def world_entry(name, arenas, age, label):
+        r = time_world(ctx, name, arenas, min(K, 50), W, age, args.seed)
+        B, gbs, frac = roofline_of(r["world"], arenas, r["ms_per_launch"], peak)
+        A = r["world"]["num_agents"]
+        e = {"config": label, "arenas_per_gpu": arenas, "episode_age_steps": age, "us": r["ms_per_launch"] * 1e3,
+             "env_steps_per_s": ctx.world * arenas / (r["ms_per_launch"] * 1e-3),
+             "agent_steps_per_s": ctx.world * arenas * A / (r["ms_per_launch"] * 1e-3),
+             "bytes_per_env_step": B, "achieved_gbs": gbs, "frac": frac, "kernel": "agar_step_kernel (" + r["env"].kernel_variant + ")",
+             "clocks": sampler.region(*r["window"]) if ctx.rank == 0 else None}
+        r["env"].close()
+        del r
+        torch.cuda.empty_cache()
+        return e
+
+    extras["cfg1_world"] = world_entry("cfg1", args.arenas, args.age, "BASELINE configs[0]/[2]/[4] world: " + describe(WORLDS["cfg1"]))
+    # configs[3]: 262,144 arenas over 8 GPUs = 32,768 per GPU (25.8 GB of observations per step and GPU)
+    free, _ = torch.cuda.mem_get_info(ctx.dev)
+    n4 = CFG4_ARENAS_PER_GPU if free > 80e9 else 4096
+    extras["cfg4_world"] = world_entry("cfg4", n4, min(args.age, 200), "BASELINE configs[3] world: " + describe(WORLDS["cfg4"]))
+
+    # rl.gae + rl.make_returns at configs[2]: T=128, N=65,536, gamma .75, lambda .1 (17 B per (t, n): SURVEY.md §8d)
+    T, N = 128, 65536
+    dev = ctx.dev
+    r = torch.randn(T, N, device=dev); v = torch.randn(T + 1, N, device=dev)
+    d = (torch.rand(T, N, device=dev) < 0.01).to(torch.uint8)
+    ev = v[T].clone()
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MB > L2: evicts it between repetitions
+    for _ in range(3):
+        ab.gae_and_returns(r, v, 0.75, 0.1, dones=d, end_value=ev)
+    ms, reps = 0.0, 200  # ~70 ms of wall clock: a few clock samples fall inside
+    t0 = time.time()
+    for _ in range(reps):
+        flush.add_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ab.gae_and_returns(r, v, 0.75, 0.1, dones=d, end_value=ev); e1.record()
+        torch.cuda.synchronize(dev)
+        ms += e0.elapsed_time(e1)
+    from agarai_b200 import sharding
+    ms = sharding.max_over_ranks(ms / reps, dev)
+    nbytes = T * N * 17 + N * 8
+    extras["gae"] = {"config": "BASELINE configs[2]: rl.gae + rl.make_returns over [128, 65536] per GPU, done cut, bootstrap",
+                     "us": ms * 1e3, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9,
+                     "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "kernel": "agar_gae_tma_kernel<8,3>",
+                     "l2": "flushed by a 256 MB write between repetitions", "clocks": sampler.region(t0, time.time()) if ctx.rank == 0 else None}
+    del r, v, d, ev
+
+    # observe-only raster of the headline world (GridFeatureExtractor.extract for every agent: state read, obs written)
+    w = WORLDS["cfg2"]
+    env = ab.BatchedAgarioEnv(ab.default_config(num_arenas=args.arenas, **w), device=dev, seed=args.seed, action_config=ab.ActionConfig(8, 1, True, True))
+    obs = env.reset()
+    for _ in range(3):
+        env.observe(out_obs=obs)
+    ms = 0.0
+    t0 = time.time()
+    for _ in range(reps):
+        flush.add_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); env.observe(out_obs=obs); e1.record()
+        torch.cuda.synchronize(dev)
+        ms += e0.elapsed_time(e1)
+    ms = sharding.max_over_ranks(ms / reps, dev)
+    nbytes = args.arenas * (env.layout.words * 4 + obs[0].numel() * 4)
+    extras["observe_only"] = {"config": f"grid observation of {args.arenas} cfg2 arenas from resident state (record read + image written)",
+                              "us": ms * 1e3, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9,
+                              "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "kernel": "agar_step_kernel (F_OBS|F_READONLY)",
+                              "l2": "flushed by a 256 MB write between repetitions", "clocks": sampler.region(t0, time.time()) if ctx.rank == 0 else None}
+    env.close()
+    return extras
+
+
 def run_cuda(args):
     import numpy as np
-    import torch
-    import torch.distributed as dist
     import agarai_b200 as ab
     from agarai_b200 import sharding
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback; use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    N = args.arenas
-    ac = ab.ActionConfig(8, 1, True, True)
-    shard = sharding.shard_from_env(N)  # rank r owns global arenas [r*N, (r+1)*N): no data-path collective
-    cfg = ab.default_config(num_arenas=N, arena_id_base=shard.arena_id_base, **WORLD)
-    env = ab.BatchedAgarioEnv(cfg, device=dev, seed=args.seed, action_config=ac)
+    ctx = _Ctx()
+    torch = ctx.torch
+    N, A = args.arenas, WORLD["num_agents"]
     K, W = args.steps, max(args.warmup, 3)
-    gen = torch.Generator(device=dev); gen.manual_seed(args.seed + rank)
-    A = WORLD["num_agents"]
-    idx = torch.randint(0, env.num_actions, (K + W, N, A), generator=gen, device=dev, dtype=torch.int32)
-    obs = [torch.empty(env.obs_shape, dtype=torch.float32, device=dev) for _ in range(2)]
-    env.reset(out_obs=obs[0])
-    if args.age > 0:  # fast-forward every arena to a fixed episode age with the same random policy (untimed)
-        ga = torch.Generator(device=dev); ga.manual_seed(args.seed + 1000 + rank)
-        for t in range(args.age):
-            ia = torch.randint(0, env.num_actions, (N, A), generator=ga, device=dev, dtype=torch.int32)
-            env.step_discrete(ia, out_obs=obs[t & 1], want_obs=not args.no_obs)
-        torch.cuda.synchronize(dev)
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(ctx.local_rank)
+    if ctx.rank == 0:
         sampler.start()
-    for i in range(W):
-        env.step_discrete(idx[i], out_obs=obs[i & 1], want_obs=not args.no_obs)
-    barrier()
-    sampler.mark_begin()
-    l0 = env.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        _, rew, done, _ = env.step_discrete(idx[W + i], out_obs=obs[i & 1], want_obs=not args.no_obs)
-    e1.record()
-    barrier()
-    sampler.mark_end()
-    ms = e0.elapsed_time(e1)
-    launches = env.launch_count - l0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_max = sharding.max_over_ranks(ms, dev)
-    value = world * N * K / (ms_max * 1e-3)
 
-    # ---- e2e: host buffers through agar_step_host (H2D actions, D2H obs/reward/done inside) ----
-    xy_tab, act_tab = ab.ppo_action_table(ac)
+    r = time_world(ctx, None, N, K, W, args.age, args.seed, no_obs=args.no_obs, want_young=args.age > 0)
+    env, idx = r["env"], r["idx"]
+    ms_launch, launches, young_ms = r["ms_per_launch"], r["launches"], r.get("young_ms_per_launch")
+    value = ctx.world * N / (ms_launch * 1e-3)
+    clocks = sampler.region(*r["window"]) if ctx.rank == 0 else None
+
+    # ---- e2e: host buffers through agar_step_host (H2D actions, D2H obs/reward/done inside), same aged arenas ----
+    xy_tab, act_tab = ab.ppo_action_table(ab.ActionConfig(8, 1, True, True))
     Ke = max(2, min(K, args.e2e_steps))
     h_idx = idx[W:W + Ke].cpu().numpy()
     h_xy = torch.from_numpy(np.ascontiguousarray(xy_tab[h_idx])).pin_memory()   # [Ke,N,A,2]
@@ -258,53 +402,65 @@ def run_cuda(args):
     h_rew = torch.empty((N, A), dtype=torch.float32).pin_memory()
     h_done = torch.empty((N, A), dtype=torch.uint8).pin_memory()
     env.step_host(h_xy[0].numpy(), h_act[0].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())  # warm-up
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
     for i in range(Ke):
         env.step_host(h_xy[i].numpy(), h_act[i].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())
-    torch.cuda.synchronize(dev)
-    e2e_value = world * N * Ke / sharding.max_over_ranks(time.perf_counter() - t0, dev)
+    torch.cuda.synchronize(ctx.dev)
+    e2e_local = time.perf_counter() - t0
+    e2e_value = ctx.world * N * Ke / sharding.max_over_ranks(e2e_local, ctx.dev)
     h2d = N * A * (8 + 4)
     d2h = h_obs.numel() * 4 + N * A * (4 + 1)
+    e2e_gbs_local = (h2d + d2h) * Ke / e2e_local / 1e9
+    obs_mb = h_obs.numel() * 4 / 1e6
+    state_mb = env.layout.words * 4 * N / 1e6
+    env.close()
+    del r, env, h_obs
+    torch.cuda.empty_cache()
 
-    if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        B = algorithmic_bytes_per_env_step()
-        launch_s = (ms_max * 1e-3) / max(launches, 1)
-        achieved = B * N / launch_s / 1e9
+    peak, peak_src = measured_peak_gbs()
+    extras = None if (args.no_extras or args.set or args.no_obs) else run_extras(ctx, args, sampler, peak)
+
+    if ctx.rank == 0:
+        B, achieved, frac = roofline_of(WORLD, N, ms_launch, peak)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": K, "warmup": W,
+            "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.world}: {N} arenas/GPU, {A} agent(s) + {WORLD['num_bots']} bots + "
-                                   f"{WORLD['num_viruses']} viruses, {WORLD['num_pellets']} pellets, arena "
-                                   f"{WORLD['arena_size']:g}, obs {bin(WORLD['obs_flags']).count('1')}x{WORLD['grid_size']}x{WORLD['grid_size']} f32 per agent, random policy over 25 actions "
-                                   "(8 dirs, split, feed)",
-                       "arenas_per_gpu": N,
-                       "l2": f"no flush: each step streams {env.layout.words * 4 * N / 1e6:.0f} MB of state and writes "
-                             f"a {obs[0].numel() * 4 / 1e6:.0f} MB observation buffer (2 alternate); L2 is 126 MB",
+            "config": {"workload": f"{args.world}: {N} arenas/GPU, {describe(WORLD)}, random policy over 25 actions (8 dirs, split, feed)",
+                       "arenas_per_gpu": N, "episode_age_steps": args.age,
+                       "l2": f"no flush: each step streams {state_mb:.0f} MB of state and writes a {obs_mb:.0f} MB observation "
+                             "buffer (2 alternate); L2 is 126 MB",
                        **WORLD},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "api": "agar_step_host (pinned host buffers; obs D2H every step, 4 chunks: copy of one overlaps the kernel of the next)"},
+                    "steps": Ke, "host_gbs_rank0": e2e_gbs_local,
+                    "api": "agar_step_host (pinned host buffers; obs D2H every step, 4 chunks: copy of one overlaps the kernel of the next)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_bytes(args.world, N) if not args.set else None, "kernel": "agar_step_kernel", "bytes_per_env_step": B,
-                         "env_steps_per_launch": N, "launch_us": launch_s * 1e6, "peak_source": peak_src},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": frac,
+                         "traffic": ncu_traffic_bytes(args.world, N) if not args.set else None, "kernel": "agar_step_kernel",
+                         "bytes_per_env_step": B, "env_steps_per_launch": N, "launch_us": ms_launch * 1e3, "peak_source": peak_src},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if young_ms is not None:  # the regime round 1 reported: the first steps after a reset
+            _, yg, yf = roofline_of(WORLD, N, young_ms, peak)
+            line["young_world"] = {"episode_age_steps": 0, "value": ctx.world * N / (young_ms * 1e-3), "unit": UNIT,
+                                   "launch_us": young_ms * 1e3, "frac": yf}
+        if extras is not None:
+            line["extras"] = extras
+        if ctx.world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sample = 512
-            _, sec = cpu_arm(sample, 1, 1, cores)        # size the sample for ~10-20 s of CPU work
-            steps_cpu = int(max(3, min(200, 12.0 / max(sec, 1e-3))))
-            v, sec = cpu_arm(sample, steps_cpu, 1, cores)
+            _, sec, _ = cpu_arm(sample, 1, 1, cores)        # size the sample for ~10 s of timed CPU work
+            steps_cpu = int(max(3, min(100, 8.0 / max(sec, 1e-3))))
+            v, sec, t_age = cpu_arm(sample, steps_cpu, 1, cores, age=args.age)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{sample} arenas x {steps_cpu} steps of the same world, "
-                                              "oracle/agar_oracle.c, one pthread per core"}
+                                    "sample": f"{sample} arenas x {steps_cpu} steps of the same world after {args.age} untimed ageing "
+                                              f"steps ({t_age:.0f} s), oracle/agar_oracle.c, one pthread per core"}
         print(json.dumps(line), flush=True)
-    env.close()
-    if world > 1:
-        dist.destroy_process_group()
+    sampler.stop()
+    if ctx.world > 1:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -317,7 +473,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--age", type=int, default=0, help="untimed steps run before the warm-up (episode age of the timed region)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg1 / cfg4 / GAE / observe-only extras")
+    ap.add_argument("--age", type=int, default=DEFAULT_AGE,
+                    help="untimed steps run before the warm-up in both arms (episode age of the timed region); 0 = right after reset")
     ap.add_argument("--no-obs", action="store_true", help="tuning only: step without the observation raster")
     ap.add_argument("--world", default="cfg2", choices=sorted(WORLDS), help="BASELINE.json world (default: the headline cfg2)")
     ap.add_argument("--set", action="append", default=[], metavar="FIELD=VALUE",

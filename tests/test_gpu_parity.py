@@ -619,9 +619,9 @@ def test_per_config_specialised_library_build(oracle):
     env.close()
 
 
-def test_crowded_arena_eat_test_through_bin_heads(oracle):
-    """More than 32 cells in an arena switch the cell-eats-cell test from scanning every alive cell to the per-bin
-    candidate heads + overflow list: many split cells of several players in a small arena, eats every few ticks."""
+def test_crowded_arena_eat_test(oracle):
+    """More than 32 alive cells in an arena: the motion / pellet-query and cell-eats-cell phases (8 cells per warp pass,
+    four warps) take a second pass.  Many split cells of several players in a small arena, eats every few ticks."""
     genv, oenv = make_pair(oracle, seed=17, num_arenas=6, num_agents=6, num_bots=6, num_viruses=2, num_pellets=300,
                            arena_size=260.0, grid_size=16, obs_flags=7, event_capacity=4096, auto_reset=1, start_mass=300.0,
                            split_min_mass=20.0, merge_delay=40.0, speed_k=5.0, virus_pop_mass=1e9)
@@ -631,3 +631,35 @@ def test_crowded_arena_eat_test_through_bin_heads(oracle):
     assert counts[4] > 20 and counts[6] > 100, counts          # cell-eaten and split events
     assert ((st[:, L.cell_m:L.cell_m + L.cells_total] > 0).sum(1) > 32).any(), "no arena stayed crowded"
     genv.close()
+
+
+def test_aged_cfg2_world_lockstep(oracle):
+    """The regime a training run lives in (bench.py `episode_age_steps`): the BASELINE configs[1] world stepped for 1,500
+    steps with the bench's random policy, state / observations / rewards / dones compared with the oracle at every step.
+    The run must reach the states that dominate the steady-state cost: an arena with more than 40 alive cells (virus
+    pops) and a cell heavier than 1,000."""
+    import agarai_b200 as ab
+    import bench
+    n, seed = 8, 50
+    kw = dict(bench.WORLDS["cfg2"], num_arenas=n)
+    genv = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=seed, action_config=ab.ActionConfig(8, 1, True, True))
+    assert genv.kernel_variant == "cfg2"
+    oenv = oracle.OracleEnv(oracle.default_config(**kw), seed=seed, nthreads=8)
+    xy_tab, act_tab = ab.ppo_action_table(ab.ActionConfig(8, 1, True, True))
+    assert np.array_equal(genv.reset().cpu().numpy(), oenv.reset())
+    rng = np.random.default_rng(seed)
+    L = genv.layout
+    max_alive, max_mass = 0, 0.0
+    for t in range(1500):
+        idx = rng.integers(0, len(act_tab), (n, 1))
+        go, gr, gd, _ = genv.step_discrete(torch.from_numpy(idx.astype(np.int32)).cuda())
+        oo, orr, od = oenv.step(xy_tab[idx], act_tab[idx])
+        gs = genv.get_state().cpu().numpy()
+        assert np.array_equal(gs.view(np.int32), oenv.get_state().view(np.int32)), f"state, step {t}"
+        assert np.array_equal(go.cpu().numpy().view(np.int32), oo.view(np.int32)), f"obs, step {t}"
+        assert np.array_equal(gr.cpu().numpy().view(np.int32), orr.view(np.int32)) and np.array_equal(gd.cpu().numpy(), od), f"step {t}"
+        m = gs[:, L.cell_m:L.cell_m + L.cells_total]
+        max_alive = max(max_alive, int((m > 0).sum(1).max()))
+        max_mass = max(max_mass, float(m.max()))
+    assert max_alive > 40 and max_mass > 1000.0, (max_alive, max_mass)
+    genv.close(); oenv.close()
