@@ -100,9 +100,10 @@ def lib():
     return _lib
 
 
-def check(rc):
+def check(rc, L=None):
+    """Raises AgarError with the message of the library `L` that returned `rc` (default: the default build)."""
     if rc != 0:
-        raise AgarError(lib().agar_last_error().decode())
+        raise AgarError((L or lib()).agar_last_error().decode())
 
 
 def default_config(**overrides):

@@ -23,11 +23,12 @@ from .actions import ActionConfig, ppo_action_table
 
 OBS_PELLETS, OBS_CELLS, OBS_OTHERS, OBS_VIRUSES, OBS_FOODS = 1, 2, 4, 8, 16
 
-# gym ids the reference uses (configuration/__init__.py:38-42, dqn/hyperparameters.py:89)
-GYM_IDS = ("agario-grid-v0", "agario-ram-v0")
+# gym ids the reference uses (configuration/__init__.py:38-42, dqn/hyperparameters.py:89); "full" hands out the raw
+# entity lists (`FullObservation`) that the reference's extractors consume (dqn/training.py:252-256)
+GYM_IDS = ("agario-grid-v0", "agario-ram-v0", "agario-full-v0")
 # screen frames are drawn by the external package's renderer (only their grayscale reduction is in the
-# reference tree: features.ScreenFeatureExtractor); "full" hands out raw entity lists, see full_observation()
-_UNSUPPORTED_IDS = ("agario-screen-v0", "agario-full-v0")
+# reference tree: features.ScreenFeatureExtractor)
+_UNSUPPORTED_IDS = ("agario-screen-v0",)
 
 # `difficulty` only selects defaults in the original package; explicit kwargs win
 _DIFFICULTY_DEFAULTS = {
@@ -72,7 +73,9 @@ def _ptr(t: Optional[torch.Tensor]):
 def config_from_gym_kwargs(num_envs=1, **kw) -> "_lib.AgarConfig":
     """Maps the reference's gym.make kwargs (configuration/__init__.py:53-71; a2c/train.py:17-64;
     old style dqn/train.py:57-67) onto an AgarConfig.  Unknown keys raise like gym would; any
-    AgarConfig field may also be passed directly to override this build's rule constants."""
+    AgarConfig field may also be passed directly to override this build's rule constants.
+    `num_frames` (environment.proto:44) is not an engine field: it is validated here and applied by
+    BatchedAgarioEnv(num_frames=...) / make(), which stack the last k grids of every agent."""
     kw = dict(kw)
     difficulty = str(kw.pop("difficulty", "normal")).lower()
     if difficulty not in _DIFFICULTY_DEFAULTS:
@@ -82,8 +85,8 @@ def config_from_gym_kwargs(num_envs=1, **kw) -> "_lib.AgarConfig":
     if "frames_per_step" in kw:  # old-style name (dqn/train.py:58)
         kw.setdefault("ticks_per_step", kw.pop("frames_per_step"))
     num_frames = int(kw.pop("num_frames", 1))
-    if num_frames != 1:
-        raise ValueError("num_frames > 1 is not supported (environment.proto:44 default is 1)")
+    if not 1 <= num_frames <= 16:
+        raise ValueError("num_frames must be in [1, 16] (environment.proto:44 default is 1)")
     flags = 0
     for key, bit in (("observe_pellets", OBS_PELLETS), ("observe_cells", OBS_CELLS),
                      ("observe_others", OBS_OTHERS), ("observe_viruses", OBS_VIRUSES),
@@ -115,29 +118,38 @@ class BatchedAgarioEnv:
     metadata = {"render.modes": []}
 
     def __init__(self, cfg: "_lib.AgarConfig", device=None, seed: int = 0, action_config: ActionConfig = None,
-                 observation: str = "grid", ram_extractor=None, lib_path: Optional[str] = None):
+                 observation: str = "grid", ram_extractor=None, lib_path: Optional[str] = None, num_frames: int = 1):
         self._h = None
         if observation not in ("grid", "ram"):
             raise ValueError("observation must be 'grid' or 'ram'")
+        if not 1 <= int(num_frames) <= 16 or (num_frames != 1 and observation != "grid"):
+            raise ValueError("num_frames must be in [1, 16] and applies to the grid observation")
+        self.num_frames = int(num_frames)
         self.observation = observation
         self._L = _lib.lib() if lib_path is None else _lib.load(lib_path)  # lib_path: a build.build_specialised() copy
         if not torch.cuda.is_available():
             raise _lib.AgarError("BatchedAgarioEnv needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         h = C.c_void_p()
-        _lib.check(self._L.agar_create(C.byref(cfg), self.device.index or 0, C.byref(h)))
+        _lib.check(self._L.agar_create(C.byref(cfg), self.device.index or 0, C.byref(h)), self._L)
         self._h = h
         self.cfg = _lib.AgarConfig()
-        _lib.check(self._L.agar_get_config(self._h, C.byref(self.cfg)))
+        _lib.check(self._L.agar_get_config(self._h, C.byref(self.cfg)), self._L)
         self.layout = _lib.AgarLayout()
-        _lib.check(self._L.agar_get_layout(self._h, C.byref(self.layout)))
+        _lib.check(self._L.agar_get_layout(self._h, C.byref(self.layout)), self._L)
         self.num_envs, self.num_agents = self.cfg.num_arenas, self.cfg.num_agents
         self.channels = self._L.agar_obs_channels(C.byref(self.cfg))
         G = self.cfg.grid_size
-        self.obs_shape = (self.num_envs, self.num_agents, self.channels, G, G)
+        # num_frames = k (environment.proto:44, own spec: the external package is absent): an observation stacks the
+        # grids of the agent's last k steps along the channel axis, oldest first; after reset() all k are the first
+        # grid.  The kernel writes each step's grid into one slot of a device ring [k, N, A, C, G, G]; the stacked
+        # tensor handed out is a fresh copy (callers keep observations, rollout/multi_rollout.py:42-44).
+        self.frame_shape = (self.num_envs, self.num_agents, self.channels, G, G)
+        self.obs_shape = (self.num_envs, self.num_agents, self.num_frames * self.channels, G, G)
+        self._ring, self._ring_pos = None, 0
         # per-agent spaces, as the reference's consumers read them (dqn/qn.py:50 takes shape[0] as
         # channels => CHW, which is also GridFeatureExtractor.shape, features/extractors.py:31)
-        self.observation_space = Box(-1.0, np.inf, (self.channels, G, G))
+        self.observation_space = Box(-1.0, np.inf, (self.num_frames * self.channels, G, G))
         self.ram_extractor = None
         if observation == "ram":  # agario-ram-v0: FeatureExtractor vectors (features/extractors.py:99-149)
             from .features import FeatureExtractor
@@ -162,7 +174,7 @@ class BatchedAgarioEnv:
             pass
 
     def seed(self, seed: int):
-        _lib.check(self._L.agar_seed(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1))))
+        _lib.check(self._L.agar_seed(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1))), self._L)
         return [seed]
 
     def _stream(self):
@@ -171,20 +183,57 @@ class BatchedAgarioEnv:
     def _new_obs(self):
         return torch.empty(self.obs_shape, dtype=torch.float32, device=self.device)
 
+    # ---- frame ring (num_frames > 1) ------------------------------------------------------
+    def _frame_slot(self, advance: bool):
+        """the ring slot the kernel writes this call's grid into"""
+        if self._ring is None:
+            self._ring = torch.zeros((self.num_frames,) + self.frame_shape, dtype=torch.float32, device=self.device)
+        if advance:
+            self._ring_pos = (self._ring_pos + 1) % self.num_frames
+        return self._ring[self._ring_pos]
+
+    def _stacked(self, out_obs):
+        """[N, A, k*C, G, G]: the ring's slots oldest first, copied out"""
+        k = self.num_frames
+        order = [(self._ring_pos + 1 + i) % k for i in range(k)]
+        out = self._new_obs() if out_obs is None else out_obs
+        N, A, C, G = self.num_envs, self.num_agents, self.channels, self.cfg.grid_size
+        torch.stack([self._ring[j] for j in order], dim=2, out=out.view(N, A, k, C, G, G))
+        return out
+
     # ---- reference interface --------------------------------------------------------------
-    def reset(self, mask: Optional[torch.Tensor] = None, out_obs: Optional[torch.Tensor] = None):
-        obs = self._new_obs() if out_obs is None else out_obs
+    def reset(self, mask: Optional[torch.Tensor] = None, out_obs: Optional[torch.Tensor] = None, want_obs: bool = True):
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         ram = self.ram_extractor is not None
-        _lib.check(self._L.agar_reset(self._h, _ptr(mask), None if ram else _ptr(obs), self._stream()))
-        return self.ram_extractor.extract(self, out=obs) if ram else obs
+        if self.num_frames > 1:
+            frame = self._frame_slot(advance=False)
+            _lib.check(self._L.agar_reset(self._h, _ptr(mask), _ptr(frame), self._stream()), self._L)
+            sel = slice(None) if mask is None else mask.bool()
+            for j in range(self.num_frames):  # a reset arena starts with k copies of its first grid
+                if j != self._ring_pos:
+                    self._ring[j][sel] = frame[sel]
+            return self._stacked(out_obs)
+        obs = (self._new_obs() if out_obs is None else out_obs) if want_obs else None
+        _lib.check(self._L.agar_reset(self._h, _ptr(mask), None if (ram or obs is None) else _ptr(obs), self._stream()), self._L)
+        return self.ram_extractor.extract(self, out=obs) if (ram and obs is not None) else obs
 
     def _outs(self, out_obs, want_obs):
-        obs = (self._new_obs() if out_obs is None else out_obs) if want_obs else None
+        """(buffer the kernel rasterises into, reward, done); with num_frames > 1 the buffer is the next ring slot"""
+        if self.num_frames > 1:
+            obs = self._frame_slot(advance=True)
+        else:
+            obs = (self._new_obs() if out_obs is None else out_obs) if want_obs else None
         reward = torch.empty((self.num_envs, self.num_agents), dtype=torch.float32, device=self.device)
         done = torch.empty((self.num_envs, self.num_agents), dtype=torch.uint8, device=self.device)
         return obs, reward, done
+
+    def _obs_out(self, obs, out_obs, want_obs):
+        if self.num_frames > 1:
+            return self._stacked(out_obs) if want_obs else None
+        if self.ram_extractor is not None and obs is not None:
+            self.ram_extractor.extract(self, out=obs)
+        return obs
 
     def step(self, target_xy: torch.Tensor, act: torch.Tensor, out_obs=None, want_obs=True):
         t = target_xy.to(device=self.device, dtype=torch.float32).contiguous()
@@ -194,16 +243,14 @@ class BatchedAgarioEnv:
         obs, reward, done = self._outs(out_obs, want_obs)
         ram = self.ram_extractor is not None
         _lib.check(self._L.agar_step(self._h, _ptr(t), _ptr(a), None if ram else _ptr(obs), _ptr(reward), _ptr(done),
-                                     self._stream()))
-        if ram and obs is not None:
-            self.ram_extractor.extract(self, out=obs)
-        return obs, reward, done, {}
+                                     self._stream()), self._L)
+        return self._obs_out(obs, out_obs, want_obs), reward, done, {}
 
     def set_action_table(self, xy: np.ndarray, act: np.ndarray):
         xy = np.ascontiguousarray(xy, np.float32)
         act = np.ascontiguousarray(act, np.int32)
         _lib.check(self._L.agar_set_action_table(self._h, xy.ctypes.data_as(C.c_void_p),
-                                                 act.ctypes.data_as(C.c_void_p), len(act)))
+                                                 act.ctypes.data_as(C.c_void_p), len(act)), self._L)
         self.num_actions = len(act)
 
     def step_discrete(self, action_index: torch.Tensor, out_obs=None, want_obs=True):
@@ -214,25 +261,26 @@ class BatchedAgarioEnv:
         obs, reward, done = self._outs(out_obs, want_obs)
         ram = self.ram_extractor is not None
         _lib.check(self._L.agar_step_indexed(self._h, _ptr(idx), None if ram else _ptr(obs), _ptr(reward), _ptr(done),
-                                             self._stream()))
-        if ram and obs is not None:
-            self.ram_extractor.extract(self, out=obs)
-        return obs, reward, done, {}
+                                             self._stream()), self._L)
+        return self._obs_out(obs, out_obs, want_obs), reward, done, {}
 
     def observe(self, out_obs=None):
+        if self.num_frames > 1:  # the current grid is already in the ring
+            return self._stacked(out_obs)
         obs = self._new_obs() if out_obs is None else out_obs
         if self.ram_extractor is not None:
             return self.ram_extractor.extract(self, out=obs)
-        _lib.check(self._L.agar_observe(self._h, _ptr(obs), self._stream()))
+        _lib.check(self._L.agar_observe(self._h, _ptr(obs), self._stream()), self._L)
         return obs
 
     def observe_records(self, state: torch.Tensor):
-        """Rasterise state snapshots ([n, layout.words] float32) kept instead of observations."""
+        """Rasterise state snapshots ([n, layout.words] float32) kept instead of observations (one grid per
+        snapshot: [n, A, C, G, G] whatever num_frames is)."""
         s = state.to(device=self.device, dtype=torch.float32).contiguous()
         n = s.shape[0]
         G = self.cfg.grid_size
         obs = torch.empty((n, self.num_agents, self.channels, G, G), dtype=torch.float32, device=self.device)
-        _lib.check(self._L.agar_observe_records(self._h, _ptr(s), n, _ptr(obs), self._stream()))
+        _lib.check(self._L.agar_observe_records(self._h, _ptr(s), n, _ptr(obs), self._stream()), self._L)
         return obs
 
     def render(self, mode="human"):
@@ -241,21 +289,21 @@ class BatchedAgarioEnv:
     # ---- state / events (parity tests, checkpoint-resume) ----------------------------------
     def get_state(self) -> torch.Tensor:
         s = torch.empty((self.num_envs, self.layout.words), dtype=torch.float32, device=self.device)
-        _lib.check(self._L.agar_get_state(self._h, _ptr(s), self._stream()))
+        _lib.check(self._L.agar_get_state(self._h, _ptr(s), self._stream()), self._L)
         return s
 
     def set_state(self, state: torch.Tensor):
         s = state.to(device=self.device, dtype=torch.float32).contiguous()
         if tuple(s.shape) != (self.num_envs, self.layout.words):
             raise ValueError("set_state: wrong shape")
-        _lib.check(self._L.agar_set_state(self._h, _ptr(s), self._stream()))
+        _lib.check(self._L.agar_set_state(self._h, _ptr(s), self._stream()), self._L)
         torch.cuda.current_stream(self.device).synchronize()  # `s` may be a temporary
 
     def events(self):
         cap = self.cfg.event_capacity
         ev = torch.zeros((self.num_envs, max(cap, 1), 4), dtype=torch.int32, device=self.device)
         cnt = torch.zeros((self.num_envs,), dtype=torch.int32, device=self.device)
-        _lib.check(self._L.agar_events(self._h, _ptr(ev), _ptr(cnt), self._stream()))
+        _lib.check(self._L.agar_events(self._h, _ptr(ev), _ptr(cnt), self._stream()), self._L)
         return ev, cnt
 
     def step_host(self, target_xy: np.ndarray, act: np.ndarray, obs: Optional[np.ndarray],
@@ -267,11 +315,16 @@ class BatchedAgarioEnv:
         if obs is not None and (obs.dtype != np.float32 or not obs.flags.c_contiguous or obs.size != int(np.prod(self.obs_shape))):
             raise ValueError("step_host: bad obs buffer")
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        if self.num_frames > 1 and obs is not None:  # stacked grids: the device ring, then one copy
+            o, r, d, _ = self.step(torch.from_numpy(target_xy), torch.from_numpy(act))
+            torch.from_numpy(obs).copy_(o.reshape(obs.shape))
+            torch.from_numpy(reward).copy_(r); torch.from_numpy(done).copy_(d)
+            return
         if self.ram_extractor is not None and obs is not None:  # feature vectors: a second launch, then one copy
-            _lib.check(self._L.agar_step_host(self._h, vp(target_xy), vp(act), None, vp(reward), vp(done)))
+            _lib.check(self._L.agar_step_host(self._h, vp(target_xy), vp(act), None, vp(reward), vp(done)), self._L)
             torch.from_numpy(obs).copy_(self.ram_extractor.extract(self).reshape(obs.shape))
             return
-        _lib.check(self._L.agar_step_host(self._h, vp(target_xy), vp(act), vp(obs), vp(reward), vp(done)))
+        _lib.check(self._L.agar_step_host(self._h, vp(target_xy), vp(act), vp(obs), vp(reward), vp(done)), self._L)
 
     @property
     def launch_count(self) -> int:
@@ -295,12 +348,15 @@ class GymCompatEnv:
     observation is all zeros where the reference extractor would give None
     (features/extractors.py:42)."""
 
-    def __init__(self, env: BatchedAgarioEnv, multi_agent: bool = True):
+    def __init__(self, env: BatchedAgarioEnv, multi_agent: bool = True, full: bool = False):
         if env.num_envs != 1:
             raise ValueError("GymCompatEnv wraps a single-arena BatchedAgarioEnv (num_envs=1)")
         self.env = env
         self.multi_agent = multi_agent
-        self.observation_space = env.observation_space
+        # `agario-full-v0` (dqn/hyperparameters.py:89): observations are `FullObservation` entity lists, which the
+        # caller feeds to a feature extractor (dqn/training.py:252-256); no grid is rasterised by the step itself
+        self.full = full
+        self.observation_space = None if full else env.observation_space
         self.action_space = env.action_space
         A = env.num_agents
         # pinned staging so the per-step copies are single async DMA transfers
@@ -318,7 +374,17 @@ class GymCompatEnv:
             return [obs_np[0, i].copy() for i in range(self.env.num_agents)]
         return obs_np[0, 0].copy()
 
+    def _full_out(self):
+        from .features import full_observation
+        rec = self.env.get_state()[0].cpu().numpy()
+        if self.multi_agent:
+            return [full_observation(self.env, 0, i, record=rec) for i in range(self.env.num_agents)]
+        return full_observation(self.env, 0, 0, record=rec)
+
     def reset(self):
+        if self.full:
+            self.env.reset(want_obs=False)
+            return self._full_out()
         obs = self.env.reset()
         return self._obs_out(obs.cpu().numpy())
 
@@ -334,8 +400,9 @@ class GymCompatEnv:
             x, y, act = actions
             self._t[0, 0, 0], self._t[0, 0, 1] = float(x), float(y)
             self._a[0, 0] = int(act)
-        self.env.step_host(self._t.numpy(), self._a.numpy(), self._obs.numpy(), self._r.numpy(), self._d.numpy())
-        obs = self._obs_out(self._obs.numpy())
+        self.env.step_host(self._t.numpy(), self._a.numpy(), None if self.full else self._obs.numpy(), self._r.numpy(),
+                           self._d.numpy())
+        obs = self._full_out() if self.full else self._obs_out(self._obs.numpy())
         if self.multi_agent:
             return obs, self._r.numpy()[0].copy(), self._d.numpy()[0].astype(bool), {}
         return obs, float(self._r[0, 0]), bool(self._d[0, 0]), {}
@@ -352,12 +419,20 @@ def make(env_id: str = "agario-grid-v0", num_envs: int = 1, device=None, seed: i
     """gym.make(env_id, **kwargs) for the batched engine.  With num_envs == 1 (and gym_compat not
     False) the reference-shaped per-arena view is returned; otherwise the batched tensor env."""
     if env_id in _UNSUPPORTED_IDS:
-        raise NotImplementedError(f"{env_id}: the grid and ram observation families are on the accelerated path")
+        raise NotImplementedError(f"{env_id}: frames come from the external package's renderer; the grid, ram and full "
+                                  "observation families are served")
     if env_id not in GYM_IDS:
         raise ValueError(f"unknown env id {env_id!r}")
-    multi_agent = bool(kwargs.get("multi_agent", True))
+    # the reference's multi-agent call sites pass multi_agent=True explicitly (configuration/__init__.py:54); the
+    # old-style single-agent ones (dqn/train.py:57-81) pass neither key and then call env.step((x, y, act))
+    multi_agent = bool(kwargs.get("multi_agent", int(kwargs.get("num_agents", 1)) > 1))
     ram_extractor = kwargs.pop("ram_extractor", None)
     specialise = bool(kwargs.pop("specialise", False))
+    num_frames = int(kwargs.get("num_frames", 1))
+    if env_id == "agario-full-v0":
+        for key in ("grid_size", "num_frames", "observe_cells", "observe_others", "observe_viruses", "observe_pellets"):
+            kwargs.pop(key, None)  # observation kwargs of the other families have no meaning here
+        num_frames = 1
     cfg = config_from_gym_kwargs(num_envs=num_envs, **kwargs)
     lib_path = None
     if specialise and cfg.event_capacity == 0:  # compile (once) a step kernel with this world's sizes as constants
@@ -365,7 +440,9 @@ def make(env_id: str = "agario-grid-v0", num_envs: int = 1, device=None, seed: i
         lib_path = _build.build_specialised(cfg)
     env = BatchedAgarioEnv(cfg, device=device, seed=seed, action_config=action_config,
                            observation="ram" if env_id == "agario-ram-v0" else "grid", ram_extractor=ram_extractor,
-                           lib_path=lib_path)
+                           lib_path=lib_path, num_frames=num_frames)
     if gym_compat is None:
         gym_compat = num_envs == 1
-    return GymCompatEnv(env, multi_agent=multi_agent) if gym_compat else env
+    if env_id == "agario-full-v0" and not gym_compat:
+        raise ValueError("agario-full-v0 hands out host-side entity lists: use it through the per-arena view (num_envs=1)")
+    return GymCompatEnv(env, multi_agent=multi_agent, full=env_id == "agario-full-v0") if gym_compat else env

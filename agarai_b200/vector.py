@@ -56,7 +56,7 @@ class Coordinator:
         self.multi_agent = bool(kw.get("multi_agent", int(kw.get("num_agents", 1)) > 1))
         kw.setdefault("auto_reset", 0)  # a finished env stays finished until reset(), as a worker's env does
         cfg = config_from_gym_kwargs(num_envs=self.num_workers, **kw)
-        self.env = BatchedAgarioEnv(cfg, device=self.device, seed=self.seed)
+        self.env = BatchedAgarioEnv(cfg, device=self.device, seed=self.seed, num_frames=int(kw.get("num_frames", 1)))
         N, A = self.num_workers, self.env.num_agents
         self._t = torch.zeros((N, A, 2), dtype=torch.float32).pin_memory()
         self._a = torch.zeros((N, A), dtype=torch.int32).pin_memory()

@@ -75,8 +75,9 @@ def test_gym_kwargs_mapping():
     assert dqn.ticks_per_step == 4 and dqn.num_agents == 1
     with pytest.raises(TypeError):
         ab.config_from_gym_kwargs(no_such_kwarg=1)
+    assert ab.config_from_gym_kwargs(num_frames=4).grid_size == 64  # validated here, applied by the env (frame ring)
     with pytest.raises(ValueError):
-        ab.config_from_gym_kwargs(num_frames=4)
+        ab.config_from_gym_kwargs(num_frames=0)
     with pytest.raises(NotImplementedError):
         ab.make("agario-screen-v0")
     with pytest.raises(ValueError):
