@@ -175,6 +175,7 @@ class BatchedAgarioEnv:
 
     def seed(self, seed: int):
         _lib.check(self._L.agar_seed(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1))), self._L)
+        self.seed_value = int(seed)
         return [seed]
 
     def _stream(self):

@@ -347,14 +347,14 @@ def test_large_batch_properties(oracle):
 
 def test_ppo_loop_runs_and_snapshots_rerasterise_exactly(oracle):
     """configs[2] shape at test size: rollout with GAE on the GPU, SGD on minibatches whose
-    observations are re-rasterised from state snapshots; the re-rasterised observations equal the
+    observations are re-rasterised from state snapshots (keep="state"); the re-rasterised observations equal the
     ones the step produced."""
     import agarai_b200 as ab
     from agarai_b200 import ppo
     env = ab.BatchedAgarioEnv(ab.default_config(num_arenas=32, num_agents=1, obs_flags=7, auto_reset=1,
                                                 arena_size=200.0, num_pellets=300, grid_size=32), seed=3,
                               action_config=ab.ActionConfig(8, 1))
-    tr = ppo.PPOTrainer(env, ppo.PPOConfig(episode_length=16, num_sgd_steps=2, batch_size=64, num_features=64), seed=0)
+    tr = ppo.PPOTrainer(env, ppo.PPOConfig(episode_length=16, num_sgd_steps=2, batch_size=64, num_features=64, keep="state"), seed=0)
     s0 = env.get_state()
     assert torch.equal(env.observe_records(s0), tr.obs)          # snapshot -> same observation as reset gave
     stats = tr.train_episode()
@@ -367,6 +367,97 @@ def test_ppo_loop_runs_and_snapshots_rerasterise_exactly(oracle):
     stats2 = tr.train_episode()
     assert np.isfinite(stats2["loss"]) and tr.sgd_steps == 4
     env.close()
+
+
+def test_ppo_presampled_minibatch_rows_hold_the_rollout_observations():
+    """keep="presampled" (the default): the minibatch rows are drawn before the rollout and only their observations are
+    kept; they must be exactly the observations the policy saw at those (t, b)."""
+    import agarai_b200 as ab
+    from agarai_b200 import ppo
+    env = ab.BatchedAgarioEnv(ab.default_config(num_arenas=24, num_agents=2, obs_flags=7, auto_reset=1,
+                                                arena_size=200.0, num_pellets=300, grid_size=16), seed=5,
+                              action_config=ab.ActionConfig(8, 1))
+    tr = ppo.PPOTrainer(env, ppo.PPOConfig(episode_length=12, num_sgd_steps=3, batch_size=32, num_features=32), seed=1)
+    seen = []
+    step = env.step_discrete
+    def spy(actions, **kw):
+        seen.append(tr._flat(tr.obs).clone())   # what the policy was evaluated on at this t
+        return step(actions, **kw)
+    env.step_discrete = spy
+    tr.collect()
+    hist = torch.stack(seen)                     # [T, B, C, G, G]
+    rows = 0
+    for k in range(3):
+        t_idx, b_idx, obs = tr._minibatch(k)
+        assert len(t_idx) == 32 and torch.equal(obs, hist[t_idx, b_idx])
+        rows += len(t_idx)
+    assert rows == 96 and "state" not in tr.roll and "observations" not in tr.roll
+    adv, ret = tr.advantages()
+    assert np.isfinite(tr.update(adv, ret)["loss"])
+    env.close()
+
+
+def test_ppo_reference_episode_regime_done_semantics(oracle):
+    """auto_reset = 0: the reference's episode handling (ppo/train.py:164-197, 268-290): reset per episode, PRE-step
+    dones recorded, bootstrap of finished agents zeroed, no cut inside GAE, finished agents' rows never sampled."""
+    import agarai_b200 as ab
+    from agarai_b200 import ppo
+    kw = dict(num_arenas=16, num_agents=4, num_bots=6, num_viruses=6, num_pellets=400, max_foods=16, arena_size=120.0,
+              view_size=100.0, grid_size=16, obs_flags=7, auto_reset=0, start_mass=40.0, merge_delay=12.0, virus_mass=30.0,
+              virus_pop_mass=60.0, speed_k=6.0, pop_pieces=5)
+    env = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=3, action_config=ab.ActionConfig(8, 1, True, True))
+    for keep in ("presampled", "state"):
+        tr = ppo.PPOTrainer(env, ppo.PPOConfig(episode_length=96, num_sgd_steps=2, batch_size=48, num_features=32, keep=keep), seed=0)
+        tr.collect()
+        d = tr.roll["dones"].cpu().numpy()                       # [T, B] pre-step
+        assert not d[0].any() and d.any(), "no agent finished: the test world is too gentle"
+        assert (np.diff(d.astype(np.int8), axis=0) >= 0).all()   # sticky
+        final = np.zeros(tr.B, bool)
+        dead_rows = d[-1] != 0
+        boot = tr.roll["values"][-1].cpu().numpy()
+        assert (boot[dead_rows] == 0).all()                      # ppo/train.py:189-195
+        adv, ret = tr.advantages()
+        oadv, oret = oracle.gae(tr.roll["rewards"].cpu().numpy(), tr.roll["values"].cpu().numpy(), 0.75, 0.1,
+                                end_value=tr.roll["values"][-1].cpu().numpy())   # no done cut (rl/__init__.py:94-137)
+        assert np.array_equal(adv.cpu().numpy(), oadv) and np.array_equal(ret.cpu().numpy(), oret)
+        for k in range(2):
+            t_idx, b_idx, obs = tr._minibatch(k)
+            assert len(t_idx) == 48 and (tr.roll["dones"][t_idx, b_idx] == 0).all()   # ppo/train.py:284-290
+        assert np.isfinite(tr.update(adv, ret)["loss"])
+        ep0 = env.get_state()[:, env.layout.episode_steps].view(torch.int32)
+        tr.collect()                                             # next episode starts from a reset
+        assert not tr.roll["dones"][0].any()
+    env.close()
+
+
+def test_ppo_trainer_save_resume_reproduces_the_next_episode(tmp_path):
+    """Trainer-level checkpoint (model, optimiser, schedule, env state + seed, sampling generator, torch RNG): a trainer
+    resumed from the file produces the next episode's losses and parameters bit for bit."""
+    import agarai_b200 as ab
+    from agarai_b200 import ppo
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    kw = dict(num_arenas=16, num_agents=2, num_bots=2, obs_flags=7, auto_reset=1, arena_size=150.0, num_pellets=300, grid_size=16)
+    cfg = ppo.PPOConfig(episode_length=10, num_sgd_steps=3, batch_size=32, num_features=32)
+
+    def fresh(seed):
+        env = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=11, action_config=ab.ActionConfig(8, 1, True, True))
+        return ppo.PPOTrainer(env, cfg, seed=seed)
+
+    a = fresh(0)
+    a.train_episode()
+    path = str(tmp_path / "ppo.ckpt")
+    a.save(path)
+    want = a.train_episode()
+    want_params = [p.detach().clone() for p in a.model.parameters()]
+    want_state = a.env.get_state().clone()
+    b = fresh(123).resume(path)   # different construction seed: everything must come from the file
+    got = b.train_episode()
+    assert got == want, (got, want)
+    assert all(torch.equal(x, y) for x, y in zip(want_params, b.model.parameters()))
+    assert torch.equal(want_state.view(torch.int32), b.env.get_state().view(torch.int32))
+    assert b.sgd_steps == a.sgd_steps == 6 and b.episodes == 2
+    a.env.close(); b.env.close()
 
 
 def test_raster_crowded_view_more_than_32_other_cells(oracle):
