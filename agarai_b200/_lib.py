@@ -65,6 +65,7 @@ SYMBOLS = [
     ("agar_observe_ram", C.c_int, [_P] + [C.c_int32] * 5 + [_P, _P]),
     ("agar_screen_gray", C.c_int, [_P, C.c_int64, _P, C.c_int32, _P]),
     ("agar_launch_count", C.c_int64, [_P]),
+    ("agar_host_copy_bytes", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("agar_kernel_variant", C.c_char_p, [_P]),
     ("agar_step_smem_bytes", C.c_int64, [C.POINTER(AgarConfig)]),
 ]

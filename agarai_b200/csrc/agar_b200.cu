@@ -2,12 +2,20 @@
 // host-buffer convenience call.  Built for sm_100a only (see agarai_b200/build.py).
 #include <cuda_runtime.h>
 
+#include <immintrin.h>
+#include <sched.h>
+
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/agar_b200.h"
 #include "../../include/agar_spec.h"
@@ -58,6 +66,52 @@ bool matches(const AgarConfig& c, const AgarLayout& L) {
            L.agent_done == SL::agent_done && L.tick == SL::tick && L.dyn_begin == SL::dyn_begin;
 }
 
+// Host worker threads of agar_step_host's compact copy: run(fn) calls fn(worker, workers) on every worker and returns
+// when all of them are done.
+class HostPool {
+public:
+    explicit HostPool(int n) : n_(n) {
+        for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { loop(i); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void run(const std::function<void(int, int)>& fn) {
+        std::unique_lock<std::mutex> lk(m_);
+        job_ = &fn; ++gen_; pending_ = n_;
+        cv_.notify_all();
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+private:
+    void loop(int i) {
+        int seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+            if (stop_) return;
+            seen = gen_;
+            const std::function<void(int, int)>* f = job_;
+            lk.unlock();
+            (*f)(i, n_);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, int)>* job_ = nullptr;
+    int gen_ = 0, pending_ = 0;
+    bool stop_ = false;
+};
+
+constexpr int kHostChunks = 4;   // agar_step_host steps the batch in chunks: copies and host work overlap the next kernel
+constexpr int kEntryCap = 256;   // (index, value) pairs kept per agent image; a fuller image is copied whole
+
 }  // namespace
 
 struct AgarEnv {
@@ -87,6 +141,14 @@ struct AgarEnv {
     bool pending = false;        // work was enqueued on last_stream since the last agar_step_host
     bool pending_multi = false;  // ... on more than one caller stream
     bool persist_hash = true;    // AGAR_NO_PERSIST (debug switch) read once at create
+    // compact device-to-host copy of agar_step_host (obs_compact_kernel): occupied bins + centroids instead of images
+    bool host_compact = false;
+    int entry_cap = 0;
+    ObsEntry* d_entries = nullptr; int32_t* d_counts = nullptr; float* d_meta = nullptr;
+    ObsEntry* h_entries = nullptr; int32_t* h_counts = nullptr; float* h_meta = nullptr;  // pinned
+    cudaEvent_t chunk_done[kHostChunks] = {};
+    HostPool* pool = nullptr;
+    int64_t last_h2d = 0, last_d2h = 0;  // bytes the last agar_step_host call moved over PCIe
 };
 
 namespace {
@@ -110,6 +172,78 @@ int launch(AgarEnv* e, KArgs& a, int n_records, cudaStream_t st, bool caller_str
     e->launches += 1;
     if (caller_stream) note_stream(e, st);
     return 0;
+}
+
+// ---- host side of the compact copy: rebuild one agent's dense grid from its centroid and its occupied bins ----
+// non-temporal copy of one channel image (no read-for-ownership of the destination lines); n % 16 == 0, src 64-byte aligned
+__attribute__((target("avx512f"))) void stream_out_avx512(float* dst, const float* src, int n) {
+    for (int i = 0; i < n; i += 16) _mm512_stream_ps(dst + i, _mm512_load_ps(src + i));
+}
+__attribute__((target("avx2"))) void stream_out_avx2(float* dst, const float* src, int n) {
+    for (int i = 0; i < n; i += 8) _mm256_stream_ps(dst + i, _mm256_load_ps(src + i));
+}
+void stream_out_sse2(float* dst, const float* src, int n) {
+    for (int i = 0; i < n; i += 4) _mm_stream_ps(dst + i, _mm_load_ps(src + i));
+}
+inline void stream_out(float* dst, const float* src, int n) {  // n = G*G, a multiple of 16
+    static const int isa = __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+    const uintptr_t d = reinterpret_cast<uintptr_t>(dst);
+    if (isa == 2 && (d & 63u) == 0) stream_out_avx512(dst, src, n);
+    else if (isa >= 1 && (d & 31u) == 0) stream_out_avx2(dst, src, n);
+    else if ((d & 15u) == 0) stream_out_sse2(dst, src, n);
+    else std::memcpy(dst, src, (size_t)n * sizeof(float));
+}
+
+// Same rule as the raster (features/extractors.py:84-96): grid index i is out of bounds when its world corner is.
+// Each channel is assembled in a cache-resident staging image (base rows, then the channel's occupied bins) and
+// leaves with non-temporal stores: the destination lines are written once and never read.
+void expand_agent(const DevParams& p, float* dst, const ObsEntry* ent, int count, const float* meta) {
+    const int G = p.c.grid_size, GG = G * G, C = p.C, flags = p.c.obs_flags;
+    const float cx = meta[0], cy = meta[1], arena = p.c.arena_size;
+    const bool alive = meta[2] != 0.0f;
+    int sentmask = 0;
+    {
+        int ch = 0;
+        if (flags & AGAR_OBS_PELLETS) { sentmask |= 1 << ch; ++ch; }
+        if (flags & AGAR_OBS_CELLS) { sentmask |= 1 << ch; ++ch; }
+        if (flags & AGAR_OBS_OTHERS) { if (p.K > 1) sentmask |= 1 << ch; ++ch; }  // no sentinel pass without others
+        if (flags & AGAR_OBS_VIRUSES) { sentmask |= 1 << ch; ++ch; }
+        if (flags & AGAR_OBS_FOODS) { sentmask |= 1 << ch; ++ch; }
+    }
+    const int smask = alive ? sentmask : 0;  // an agent without cells observes zeros
+    alignas(64) float stage[128 * 128];
+    float neg_row[128], col_row[128];
+    bool oob_x[128];
+    bool any_oob = false;
+    for (int i = 0; i < G; ++i) {
+        neg_row[i] = -1.0f;
+        const float wy = p.oob_off[i] + cy, wx = p.oob_off[i] + cx;
+        col_row[i] = !(0.0f <= wy && wy < arena) ? -1.0f : 0.0f;
+        oob_x[i] = !(0.0f <= wx && wx < arena);
+        any_oob = any_oob || oob_x[i] || col_row[i] != 0.0f;
+    }
+    for (int ch = 0; ch < C; ++ch) {
+        std::memset(stage, 0, (size_t)GG * sizeof(float));
+        if (((smask >> ch) & 1) && any_oob)
+            for (int gx = 0; gx < G; ++gx) std::memcpy(stage + (size_t)gx * G, oob_x[gx] ? neg_row : col_row, (size_t)G * sizeof(float));
+        const uint32_t lo = (uint32_t)ch * (uint32_t)GG;
+        for (int e = 0; e < count; ++e) {
+            const uint32_t rel = ent[e].idx - lo;
+            if (rel < (uint32_t)GG) stage[rel] = ent[e].val;
+        }
+        stream_out(dst + (size_t)ch * GG, stage, GG);
+    }
+    _mm_sfence();
+}
+
+int host_threads_default() {
+    if (const char* v = std::getenv("AGAR_HOST_THREADS")) { const int n = std::atoi(v); if (n >= 1 && n <= 256) return n; }
+    cpu_set_t set;
+    int avail = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+    int ranks = 1;
+    if (const char* v = std::getenv("LOCAL_WORLD_SIZE")) ranks = std::atoi(v) > 0 ? std::atoi(v) : 1;  // one process per GPU share the cores
+    int n = avail / ranks;
+    return n < 1 ? 1 : (n > 32 ? 32 : n);
 }
 
 KArgs base_args(AgarEnv* e) {
@@ -260,6 +394,11 @@ int agar_destroy(AgarEnv* e) {
     if (e->host_stream2) cudaStreamDestroy(e->host_stream2);
     if (e->host_event) cudaEventDestroy(e->host_event);
     if (e->order_event) cudaEventDestroy(e->order_event);
+    delete e->pool;
+    cudaFree(e->d_entries); cudaFree(e->d_counts); cudaFree(e->d_meta);
+    cudaFreeHost(e->h_entries); cudaFreeHost(e->h_counts); cudaFreeHost(e->h_meta);
+    for (int k = 0; k < kHostChunks; ++k)
+        if (e->chunk_done[k]) cudaEventDestroy(e->chunk_done[k]);
     delete e;
     return 0;
 }
@@ -420,6 +559,26 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
         e->d_target = t; e->d_act = ac; e->d_reward = rw; e->d_done = dn;
     }
     if (h_obs && !e->d_obs) CUDA_OK(cudaMalloc(&e->d_obs, obs_elems(e) * sizeof(float)));
+    const size_t per_agent = (size_t)e->p.C * e->p.c.grid_size * e->p.c.grid_size, per_arena = A * per_agent;
+    // Compact copy (default for batches of at least 256 agents; AGAR_HOST_DENSE=1 keeps the plain image copy): the
+    // images stay on the device, the host receives each agent's centroid and occupied bins and rebuilds the dense
+    // grids with its own threads.  201 MB -> 8.5 MB over PCIe per step of 4096 cfg2 arenas.
+    if (h_obs && !e->entry_cap && NA >= 256 && !std::getenv("AGAR_HOST_DENSE")) {
+        const int cap = per_agent < (size_t)kEntryCap ? (int)per_agent : kEntryCap;
+        cudaError_t err = cudaMalloc(&e->d_entries, NA * cap * sizeof(ObsEntry));
+        if (err == cudaSuccess) err = cudaMalloc(&e->d_counts, NA * sizeof(int32_t));
+        if (err == cudaSuccess) err = cudaMalloc(&e->d_meta, NA * 4 * sizeof(float));
+        if (err == cudaSuccess) err = cudaMallocHost(&e->h_entries, NA * cap * sizeof(ObsEntry));
+        if (err == cudaSuccess) err = cudaMallocHost(&e->h_counts, NA * sizeof(int32_t));
+        if (err == cudaSuccess) err = cudaMallocHost(&e->h_meta, NA * 4 * sizeof(float));
+        for (int k = 0; k < kHostChunks && err == cudaSuccess; ++k) err = cudaEventCreateWithFlags(&e->chunk_done[k], cudaEventDisableTiming);
+        if (err != cudaSuccess) return fail(std::string("agar_step_host: compact-copy allocation failed: ") + cudaGetErrorString(err));
+        e->pool = new (std::nothrow) HostPool(host_threads_default());
+        if (!e->pool) return fail("out of host memory");
+        e->entry_cap = cap;
+        e->host_compact = true;
+    }
+    const bool compact = h_obs && e->host_compact;
     // The private streams are non-blocking: order them after whatever the caller enqueued on its own stream(s)
     // (agar_reset, agar_step, agar_set_state ...) since the previous host-buffer step.
     if (e->pending) {
@@ -431,29 +590,67 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
         e->pending = false; e->pending_multi = false;
     }
     cudaStream_t st = e->host_stream, st2 = e->host_stream2;
+    e->last_h2d = (int64_t)(NA * 2 * sizeof(float) + NA * sizeof(int32_t));
+    e->last_d2h = (int64_t)(NA * sizeof(float) + NA);
     CUDA_OK(cudaMemcpyAsync(e->d_target, h_target_xy, NA * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(e->d_act, h_act, NA * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    // The observation copy (48 KB per agent) dominates: the batch is stepped in chunks so that the device-to-host
-    // copy of one chunk (copy stream) overlaps the kernel of the next (compute stream).
-    const size_t per_arena = A * (size_t)e->p.C * e->p.c.grid_size * e->p.c.grid_size;
-    const int chunks = (h_obs && N >= 1024) ? 4 : 1;
+    // The batch is stepped in chunks so that the device-to-host copy of one chunk (copy stream), and the host's work on
+    // it, overlap the kernel of the next (compute stream).
+    const int chunks = (h_obs && N >= 1024) ? kHostChunks : 1;
+    const int cap = e->entry_cap;
     for (int k = 0; k < chunks; ++k) {
         const int a0 = (int)(N * k / chunks), a1 = (int)(N * (k + 1) / chunks);
         KArgs a = base_args(e);
         a.flags = F_STEP | (h_obs ? F_OBS : 0);
         a.target_xy = e->d_target; a.act = e->d_act; a.obs = h_obs ? e->d_obs : nullptr;
+        a.obs_meta = compact ? e->d_meta : nullptr;
         a.reward = e->d_reward; a.done = e->d_done;
         a.arena0 = a0;
         if (int rc = launch(e, a, a1 - a0, st, false)) return rc;
-        if (h_obs) {
-            CUDA_OK(cudaEventRecord(e->host_event, st));
-            CUDA_OK(cudaStreamWaitEvent(st2, e->host_event, 0));
+        if (!h_obs) continue;
+        const size_t g0 = (size_t)a0 * A, gn = (size_t)(a1 - a0) * A;  // agents of this chunk
+        if (compact) {
+            obs_compact_kernel<<<(unsigned)gn, 256, 0, st>>>(e->d_obs + g0 * per_agent, (int)per_agent, cap, e->d_entries + g0 * cap,
+                                                             e->d_counts + g0);
+            CUDA_OK(cudaGetLastError());
+            e->launches += 1;
+        }
+        CUDA_OK(cudaEventRecord(e->host_event, st));
+        CUDA_OK(cudaStreamWaitEvent(st2, e->host_event, 0));
+        if (compact) {
+            CUDA_OK(cudaMemcpyAsync(e->h_entries + g0 * cap, e->d_entries + g0 * cap, gn * cap * sizeof(ObsEntry), cudaMemcpyDeviceToHost, st2));
+            CUDA_OK(cudaMemcpyAsync(e->h_counts + g0, e->d_counts + g0, gn * sizeof(int32_t), cudaMemcpyDeviceToHost, st2));
+            CUDA_OK(cudaMemcpyAsync(e->h_meta + g0 * 4, e->d_meta + g0 * 4, gn * 4 * sizeof(float), cudaMemcpyDeviceToHost, st2));
+            CUDA_OK(cudaEventRecord(e->chunk_done[k], st2));
+            e->last_d2h += (int64_t)(gn * cap * sizeof(ObsEntry) + gn * sizeof(int32_t) + gn * 4 * sizeof(float));
+        } else {
+            e->last_d2h += (int64_t)((size_t)(a1 - a0) * per_arena * sizeof(float));
             CUDA_OK(cudaMemcpyAsync(h_obs + a0 * per_arena, e->d_obs + a0 * per_arena, (size_t)(a1 - a0) * per_arena * sizeof(float),
                                     cudaMemcpyDeviceToHost, st2));
         }
     }
     CUDA_OK(cudaMemcpyAsync(h_reward, e->d_reward, NA * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaMemcpyAsync(h_done, e->d_done, NA, cudaMemcpyDeviceToHost, st));
+    if (compact) {
+        for (int k = 0; k < chunks; ++k) {  // rebuild the dense grids of a chunk as soon as its lists have landed
+            const size_t g0 = (size_t)(N * k / chunks) * A, g1 = (size_t)(N * (k + 1) / chunks) * A;
+            CUDA_OK(cudaEventSynchronize(e->chunk_done[k]));
+            const AgarEnv* ce = e;
+            const std::function<void(int, int)> job = [ce, g0, g1, cap, per_agent, h_obs](int w, int nw) {
+                for (size_t g = g0 + (size_t)w; g < g1; g += (size_t)nw) {
+                    const int cnt = ce->h_counts[g];
+                    if (cnt > cap) continue;  // overflowed list: the image is copied whole below
+                    expand_agent(ce->p, h_obs + g * per_agent, ce->h_entries + g * cap, cnt, ce->h_meta + g * 4);
+                }
+            };
+            e->pool->run(job);
+            for (size_t g = g0; g < g1; ++g)
+                if (e->h_counts[g] > cap) {
+                    CUDA_OK(cudaMemcpyAsync(h_obs + g * per_agent, e->d_obs + g * per_agent, per_agent * sizeof(float), cudaMemcpyDeviceToHost, st2));
+                    e->last_d2h += (int64_t)(per_agent * sizeof(float));
+                }
+        }
+    }
     CUDA_OK(cudaStreamSynchronize(st));
     CUDA_OK(cudaStreamSynchronize(st2));
     return 0;
@@ -540,6 +737,12 @@ int agar_screen_gray(const uint8_t* d_rgb, int64_t n_pixels, void* d_out, int32_
 }
 
 int64_t agar_launch_count(const AgarEnv* e) { return e ? e->launches : 0; }
+
+int agar_host_copy_bytes(const AgarEnv* e, int64_t* h2d, int64_t* d2h) {
+    if (!e || !h2d || !d2h) return fail("NULL argument");
+    *h2d = e->last_h2d; *d2h = e->last_d2h;
+    return 0;
+}
 const char* agar_kernel_variant(const AgarEnv* e) { return e ? e->kernel_name : ""; }
 
 int64_t agar_step_smem_bytes(const AgarConfig* cfg) {

@@ -50,6 +50,36 @@ __global__ void __launch_bounds__(256) screen_gray_kernel(const uint8_t* __restr
     }
 }
 
+// ------------------------------------------------------------------------------ compact observations
+// agar_step_host hands dense float32 grids to a host buffer.  An agent's grid (C x G x G, 48 KB at 3 x 64 x 64) is a
+// base image of zeros and -1 sentinels plus ~100 occupied bins, and the sentinels follow from the agent's centroid
+// (obs_meta, written by the raster).  This kernel lists the entries of an image that are neither +0.0 nor -1.0 as
+// (index, value) pairs; the host copies the lists (a few KB per agent) instead of the images and rebuilds the dense
+// grids with its own threads.  One CTA per agent; the order of the pairs is arbitrary (indices are distinct).
+struct ObsEntry { uint32_t idx; float val; };
+__global__ void __launch_bounds__(256) obs_compact_kernel(const float* __restrict__ obs, int floats_per_agent, int cap,
+                                                         ObsEntry* __restrict__ entries, int32_t* __restrict__ counts) {
+    __shared__ int cnt;
+    const int tid = threadIdx.x, agent = blockIdx.x;
+    if (tid == 0) cnt = 0;
+    __syncthreads();
+    const float4* img = reinterpret_cast<const float4*>(obs + (size_t)agent * floats_per_agent);
+    ObsEntry* out = entries + (size_t)agent * cap;
+    auto emit = [&](uint32_t idx, float v) {
+        const uint32_t bits = __float_as_uint(v);
+        if (bits != 0u && bits != 0xBF800000u) {  // not +0.0, not -1.0 (bit patterns: the copy must be exact)
+            const int pos = atomicAdd(&cnt, 1);
+            if (pos < cap) { ObsEntry e; e.idx = idx; e.val = v; out[pos] = e; }
+        }
+    };
+    for (int i = tid; i < floats_per_agent / 4; i += 256) {
+        const float4 v = __ldcs(img + i);
+        emit(4u * i, v.x); emit(4u * i + 1u, v.y); emit(4u * i + 2u, v.z); emit(4u * i + 3u, v.w);
+    }
+    __syncthreads();
+    if (tid == 0) counts[agent] = cnt;  // > cap: the list overflowed and the host copies this agent's image instead
+}
+
 // ------------------------------------------------------------------------------ RAM-style features
 struct RamParams {
     int n_pellet, n_virus, n_food, n_other, n_cell;  // FeatureExtractor.__init__ (features/extractors.py:101-106)

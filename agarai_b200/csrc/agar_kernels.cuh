@@ -65,6 +65,7 @@ struct KArgs {
     const int32_t* tab_act;    // [n_actions]
     int32_t n_actions;
     float* obs;              // [N,A,C,G,G] or null
+    float* obs_meta;         // [N,A,4] or null: per agent (centroid x, y, has cells, 0), for agar_step_host's compact copy
     float* reward;           // [N,A]
     uint8_t* done;           // [N,A]
     const uint8_t* reset_mask;  // [N] or null (= all) — only read when F_RESET
@@ -622,7 +623,8 @@ __device__ __forceinline__ void count_entity(const DevParams& p, float* __restri
 // channels (pellets, viruses, foods) by float reductions of 1.0 in global memory, mass channels (own
 // cells, others) by warp 0 with sums taken in entity order.
 template <class CV>
-__device__ void raster_arena(const DevParams& p, const Smem& s, float* __restrict__ obs_arena, bool use_hash, int nlist) {
+__device__ void raster_arena(const DevParams& p, const Smem& s, float* __restrict__ obs_arena, float* __restrict__ meta_arena,
+                             bool use_hash, int nlist) {
     decltype(auto) L = layout_of<CV>(p);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const int hbase = lane & 16, slot = lane & 15;
@@ -667,6 +669,9 @@ __device__ void raster_arena(const DevParams& p, const Smem& s, float* __restric
     const int gy_t = (4 * tid) % G, gx_t = (4 * tid) / G, rstep = (4 * nt) / G;
     const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), neg4 = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
     __syncthreads();
+    if (meta_arena)  // what the host needs to rebuild an agent's sentinel rows / columns (agar_step_host)
+        for (int a = tid; a < A; a += nt)
+            *reinterpret_cast<float4*>(meta_arena + 4 * a) = make_float4(s.Cx[a], s.Cy[a], s.palive[a] ? 1.0f : 0.0f, 0.0f);
 
     for (int a = 0; a < A; ++a) {
         const float cx = s.Cx[a], cy = s.Cy[a];
@@ -1512,7 +1517,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     if ((a.flags & F_OBS) && a.obs) {
         __syncthreads();
         const int GG = G * G;
-        raster_arena<CV>(p, s, a.obs + (size_t)arena * A * CV_INT(C, p.C) * GG, s.sc[SC_HASHOK] != 0 && s.sc[SC_REBUILD] == 0,
+        raster_arena<CV>(p, s, a.obs + (size_t)arena * A * CV_INT(C, p.C) * GG, a.obs_meta ? a.obs_meta + (size_t)arena * A * 4 : nullptr,
+                         s.sc[SC_HASHOK] != 0 && s.sc[SC_REBUILD] == 0,
                          ((a.flags & F_STEP) && !static_dirty && KC > 256) ? s.sc[SC_NLIST] : -1);  // (few slots: the scan is as fast)
     }
     PHASE(15);  // raster

@@ -327,6 +327,12 @@ class BatchedAgarioEnv:
             return
         _lib.check(self._L.agar_step_host(self._h, vp(target_xy), vp(act), vp(obs), vp(reward), vp(done)), self._L)
 
+    def host_copy_bytes(self):
+        """(host->device, device->host) bytes of the last step_host call"""
+        h2d, d2h = C.c_int64(0), C.c_int64(0)
+        _lib.check(self._L.agar_host_copy_bytes(self._h, C.byref(h2d), C.byref(d2h)), self._L)
+        return int(h2d.value), int(d2h.value)
+
     @property
     def launch_count(self) -> int:
         return int(self._L.agar_launch_count(self._h))

@@ -409,9 +409,9 @@ def run_cuda(args):
     torch.cuda.synchronize(ctx.dev)
     e2e_local = time.perf_counter() - t0
     e2e_value = ctx.world * N * Ke / sharding.max_over_ranks(e2e_local, ctx.dev)
-    h2d = N * A * (8 + 4)
-    d2h = h_obs.numel() * 4 + N * A * (4 + 1)
-    e2e_gbs_local = (h2d + d2h) * Ke / e2e_local / 1e9
+    h2d, d2h = env.host_copy_bytes()            # what the last call moved over PCIe (compact copy: occupied bins, not grids)
+    delivered = h_obs.numel() * 4 + N * A * (4 + 1)   # what the caller received in its host buffers
+    e2e_gbs_local = delivered * Ke / e2e_local / 1e9
     obs_mb = h_obs.numel() * 4 / 1e6
     state_mb = env.layout.words * 4 * N / 1e6
     env.close()
@@ -434,8 +434,10 @@ def run_cuda(args):
                        **WORLD},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "host_gbs_rank0": e2e_gbs_local,
-                    "api": "agar_step_host (pinned host buffers; obs D2H every step, 4 chunks: copy of one overlaps the kernel of the next)"},
+                    "steps": Ke, "host_bytes_delivered_per_step": delivered, "host_delivery_gbs_rank0": e2e_gbs_local,
+                    "api": "agar_step_host: actions from pinned host memory, dense float32 grids + rewards + dones delivered into pinned "
+                           "host buffers every step (4 chunks; grids cross PCIe as per-agent occupied-bin lists and are rebuilt by the "
+                           "library's host threads while the next chunk runs)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": frac,
                          "traffic": ncu_traffic_bytes(args.world, N) if not args.set else None, "kernel": "agar_step_kernel",

@@ -225,8 +225,13 @@ int agar_set_state(AgarEnv* env, const float* d_src, void* stream);
 int agar_events(AgarEnv* env, int32_t* d_events, int32_t* d_counts, void* stream);
 
 /* Host-buffer step for callers that keep numpy arrays (the gym-compat view): copies the
- * actions host->device, steps, copies obs/reward/done device->host and synchronises.
- * h_obs may be NULL.  Host buffers should be pinned for full PCIe speed. */
+ * actions host->device, steps, delivers obs/reward/done into the host buffers and synchronises.
+ * h_obs may be NULL.  Host buffers should be pinned for full PCIe speed.  The call is ordered
+ * after work enqueued earlier on caller streams through this handle.  For batches of 256 agents
+ * or more the dense grids do not cross PCIe: each agent's centroid and occupied bins do (a few KB
+ * instead of 48 KB at 3x64x64) and worker threads of the library rebuild the identical float32
+ * grids in h_obs (AGAR_HOST_THREADS, default: the process's cores divided by LOCAL_WORLD_SIZE;
+ * AGAR_HOST_DENSE=1 restores the plain image copy). */
 int agar_step_host(AgarEnv* env, const float* h_target_xy, const int32_t* h_act, float* h_obs,
                    float* h_reward, uint8_t* h_done);
 
@@ -266,6 +271,9 @@ int agar_screen_gray(const uint8_t* d_rgb, int64_t n_pixels, void* d_out, int32_
 
 /* number of kernel launches issued by this handle since creation (bench bookkeeping) */
 int64_t agar_launch_count(const AgarEnv* env);
+/* bytes the last agar_step_host call moved host->device and device->host (bench bookkeeping: with the compact copy the
+ * observations cross PCIe as per-agent lists of occupied bins, not as dense grids) */
+int agar_host_copy_bytes(const AgarEnv* env, int64_t* h2d_bytes, int64_t* d2h_bytes);
 /* which instantiation of the step kernel the handle launches: "generic" (sizes read at run time) or the name of a
  * compile-time specialised world ("cfg1", "cfg2", "cfg4", "a2c", "a2c_test", "dqn") */
 const char* agar_kernel_variant(const AgarEnv* env);

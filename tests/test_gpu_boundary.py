@@ -159,3 +159,43 @@ def test_num_frames_stacks_the_last_k_grids(oracle):
     s, rew, done, _ = one.step((1.0, 0.0, 0))
     assert s.shape == (8, 16, 16)
     one.close()
+
+
+@pytest.mark.parametrize("world", ["borders_multi_agent", "single_player", "dense_overflow"])
+def test_step_host_compact_copy_rebuilds_identical_grids(world):
+    """agar_step_host with batches of >= 256 agents copies per-agent lists of occupied bins + centroids and rebuilds the
+    dense grids on host threads: the host buffer must equal, bit for bit, what agar_step wrote on the device (sentinel
+    rows / columns at the borders, the K == 1 `others` channel without sentinel, agents without cells, and images
+    fuller than the list capacity, which are copied whole)."""
+    import agarai_b200 as ab
+    kw = {
+        "borders_multi_agent": dict(num_arenas=160, num_agents=3, num_bots=4, num_viruses=5, num_pellets=300, arena_size=150.0,
+                                    view_size=100.0, grid_size=32, obs_flags=31, start_mass=40.0, virus_pop_mass=60.0, virus_mass=30.0),
+        "single_player": dict(num_arenas=300, num_agents=1, num_bots=0, num_pellets=200, arena_size=90.0, view_size=128.0,
+                              grid_size=64, obs_flags=7),
+        "dense_overflow": dict(num_arenas=1100, num_agents=1, num_bots=1, num_pellets=4000, arena_size=200.0, view_size=128.0,
+                               grid_size=64, obs_flags=7),
+    }[world]
+    a = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=21)
+    b = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=21)
+    a.reset(); b.reset()
+    N, A = kw["num_arenas"], kw["num_agents"]
+    rng = np.random.default_rng(1)
+    h_obs = torch.empty(b.obs_shape, dtype=torch.float32).pin_memory()
+    h_r = torch.empty((N, A), dtype=torch.float32).pin_memory(); h_d = torch.empty((N, A), dtype=torch.uint8).pin_memory()
+    for t in range(25):
+        xy = rng.uniform(-1, 1, (N, A, 2)).astype(f32)
+        act = rng.integers(0, 3, (N, A)).astype(np.int32)
+        o, r, d, _ = a.step(torch.from_numpy(xy).cuda(), torch.from_numpy(act).cuda())
+        h_obs.fill_(7.0)  # stale content must be overwritten everywhere
+        b.step_host(xy, act, h_obs.numpy(), h_r.numpy(), h_d.numpy())
+        assert np.array_equal(h_obs.numpy().view(np.int32), o.cpu().numpy().view(np.int32)), f"{world}: obs differ at step {t}"
+        assert np.array_equal(h_r.numpy(), r.cpu().numpy()) and np.array_equal(h_d.numpy(), d.cpu().numpy())
+    h2d, d2h = b.host_copy_bytes()
+    dense = h_obs.numel() * 4
+    assert h2d == N * A * 12
+    if world == "dense_overflow":
+        assert d2h > dense // 2, "expected most images to overflow the list and be copied whole"
+    else:
+        assert d2h < dense // 4, (d2h, dense)
+    a.close(); b.close()
