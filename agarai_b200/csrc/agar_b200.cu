@@ -676,8 +676,33 @@ int agar_gae(const float* d_reward, const float* d_value, const uint8_t* d_done,
     // stages 37 us, 16 x 2 36 us, 8 x 2 39 us).  It needs whole 128-column strips and 16-byte aligned rows.
     static const bool no_tma = std::getenv("AGAR_GAE_NO_TMA") != nullptr;
     auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
-    if (!no_tma && (N % 128) == 0 && al16(d_reward) && al16(d_value) && al16(d_done)) {
-        agar_gae_tma_kernel<8, 3><<<N / 128, 128, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N);
+    if (!no_tma && (N % 16) == 0 && al16(d_reward) && al16(d_value) && al16(d_done)) {
+        static const char* tune = std::getenv("AGAR_GAE_TMA");  // tuning switch: "U,STAGES,W"
+        int tu = 8, ts = 3, tw = 128;
+        if (tune) std::sscanf(tune, "%d,%d,%d", &tu, &ts, &tw);
+        // strip width: a multiple of 16 columns (bulk copies of the done bytes), at most the CTA's thread count, chosen so
+        // that the strips fill per_sm resident CTAs on every SM evenly
+        static int sms = 0;
+        if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
+        static const int per_sm = std::getenv("AGAR_GAE_PER_SM") ? std::atoi(std::getenv("AGAR_GAE_PER_SM")) : 4;
+        auto strip_for = [&](int wmax) {
+            int s0 = (N + sms * per_sm - 1) / (sms * per_sm);
+            s0 = (s0 + 15) / 16 * 16;
+            if (s0 < 32) s0 = 32;
+            return s0 > wmax ? wmax : s0;
+        };
+#define GAE_TMA(U_, S_, W_) do { const int strip = strip_for(W_); agar_gae_tma_kernel<U_, S_, W_><<<(N + strip - 1) / strip, W_, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N, strip); } while (0)
+        if (tu == 8 && ts == 4 && tw == 128) GAE_TMA(8, 4, 128);
+        else if (tu == 8 && ts == 5 && tw == 128) GAE_TMA(8, 5, 128);
+        else if (tu == 10 && ts == 3 && tw == 128) GAE_TMA(10, 3, 128);
+        else if (tu == 4 && ts == 6 && tw == 128) GAE_TMA(4, 6, 128);
+        else if (tu == 8 && ts == 3 && tw == 64) GAE_TMA(8, 3, 64);
+        else if (tu == 8 && ts == 6 && tw == 64) GAE_TMA(8, 6, 64);
+        else if (tu == 8 && ts == 2 && tw == 256) GAE_TMA(8, 2, 256);
+        else if (tu == 8 && ts == 3 && tw == 32) GAE_TMA(8, 3, 32);
+        else if (tu == 8 && ts == 6 && tw == 32) GAE_TMA(8, 6, 32);
+        else GAE_TMA(8, 3, 128);
+#undef GAE_TMA
         CUDA_OK(cudaGetLastError());
         return 0;
     }

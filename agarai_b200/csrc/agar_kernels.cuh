@@ -1605,48 +1605,60 @@ __global__ void __launch_bounds__(256) agar_gae_kernel(const float* __restrict__
     }
 }
 
-// The same scan fed by TMA: a CTA owns 128 adjacent columns; one thread streams batches of U rows (512 B of r, 512 B
-// of v, 128 B of done per row, one bulk copy each) into a ring of STAGES shared-memory stages, completion counted on
-// an mbarrier per stage, while all 128 threads scan the stage that has landed.  The bytes in flight no longer live in
+// The same scan fed by TMA: a CTA owns W adjacent columns; warp 0 streams batches of U rows (4W B of r, 4W B
+// of v, W B of done per row, one bulk copy each) into a ring of STAGES shared-memory stages, completion counted on
+// an mbarrier per stage, while the strip's threads scan the stage that has landed.  The strip width is chosen by the host
+// so that the strips fill every SM's resident slots evenly (65,536 columns: 586 strips of 112 on 148 SMs x 4; with
+// fixed 128-column strips the SMs hold 3 or 4 CTAs and the launch lasts as long as the fuller ones).  The bytes in flight no longer live in
 // registers, so the ring can be deep (STAGES x U rows per CTA) without costing occupancy.  Needs N % 128 == 0 and
 // 16-byte aligned buffers (the host falls back to agar_gae_kernel otherwise).
-template <int U, int STAGES>
-__global__ void __launch_bounds__(128) agar_gae_tma_kernel(const float* __restrict__ r, const float* __restrict__ v,
+template <int U, int STAGES, int W>
+__global__ void __launch_bounds__(W) agar_gae_tma_kernel(const float* __restrict__ r, const float* __restrict__ v,
                                                           const uint8_t* __restrict__ done,
                                                           const float* __restrict__ end_value, float g, float cgl,
-                                                          float* __restrict__ adv, float* __restrict__ ret, int T, int N) {
-    __shared__ __align__(16) float sr[STAGES][U][128];
-    __shared__ __align__(16) float sv[STAGES][U][128];
-    __shared__ __align__(16) uint8_t sd[STAGES][U][128];
+                                                          float* __restrict__ adv, float* __restrict__ ret, int T, int N, int strip) {
+    __shared__ __align__(16) float sr[STAGES][U][W];
+    __shared__ __align__(16) float sv[STAGES][U][W];
+    __shared__ __align__(16) uint8_t sd[STAGES][U][W];
     __shared__ __align__(8) uint64_t full[STAGES];
-    const int tid = threadIdx.x, col0 = blockIdx.x * 128, n = col0 + tid;
+    const int tid = threadIdx.x, col0 = blockIdx.x * strip, n = col0 + tid;
+    const int width = N - col0 < strip ? N - col0 : strip;  // columns of this strip (a multiple of 16, <= W)
+    const bool active = tid < width;
     const bool want_v = adv != nullptr, want_d = done != nullptr;
     const int nb = (T + U - 1) / U;
-    auto issue = [&](int k) {  // batch k: rows t = T-1-k*U downwards, at most U of them, into stage k % STAGES
+    static_assert(3 * U <= 32, "one lane of warp 0 per (row, array) of a batch");
+    const int lane = tid & 31;
+    // batch k: rows t = T-1-k*U downwards, at most U of them, into stage k % STAGES.  Called by all of warp 0: lane 0
+    // posts the byte count, then lane 3u+w issues the copy of row u of array w (r, v, done), so a batch costs the warp
+    // a dozen instructions (one thread issuing all 3U copies spent ~250 on address arithmetic, and the other warps
+    // waited for it at the barrier: the kernel was bound by that, profiles/r02_notes.txt).
+    auto issue = [&](int k) {
         const int st = k % STAGES, t_hi = T - 1 - k * U, rows = t_hi + 1 < U ? t_hi + 1 : U;
-        mbar_expect_tx(&full[st], (uint32_t)rows * (512u + (want_v ? 512u : 0u) + (want_d ? 128u : 0u)));
-        for (int u = 0; u < rows; ++u) {
+        if (lane == 0) mbar_expect_tx(&full[st], (uint32_t)rows * (uint32_t)width * (4u + (want_v ? 4u : 0u) + (want_d ? 1u : 0u)));
+        __syncwarp();
+        const int u = lane / 3, w = lane - 3 * u;
+        if (u < rows && u < U) {
             const size_t off = (size_t)(t_hi - u) * N + col0;
-            bulk_g2s(&sr[st][u][0], r + off, 512u, &full[st]);
-            if (want_v) bulk_g2s(&sv[st][u][0], v + off, 512u, &full[st]);
-            if (want_d) bulk_g2s(&sd[st][u][0], done + off, 128u, &full[st]);
+            if (w == 0) bulk_g2s(&sr[st][u][0], r + off, 4u * width, &full[st]);
+            else if (w == 1) { if (want_v) bulk_g2s(&sv[st][u][0], v + off, 4u * width, &full[st]); }
+            else if (want_d) bulk_g2s(&sd[st][u][0], done + off, (uint32_t)width, &full[st]);
         }
     };
     if (tid == 0) {
         for (int st = 0; st < STAGES; ++st) mbar_init(&full[st], 1);
     }
     __syncthreads();
-    if (tid == 0)
+    if (tid < 32)
         for (int k = 0; k < STAGES && k < nb; ++k) issue(k);
     float a_next = 0.0f;
-    float g_next = end_value ? end_value[n] : 0.0f;
-    float v_next = want_v ? __ldcs(v + (size_t)T * N + n) : 0.0f;
+    float g_next = (end_value && active) ? end_value[n] : 0.0f;
+    float v_next = (want_v && active) ? __ldcs(v + (size_t)T * N + n) : 0.0f;
     for (int k = 0; k < nb; ++k) {
         const int st = k % STAGES, t_hi = T - 1 - k * U, rows = t_hi + 1 < U ? t_hi + 1 : U;
         mbar_wait(&full[st], (uint32_t)((k / STAGES) & 1));
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (u >= rows) break;
+            if (u >= rows || !active) break;
             const int t = t_hi - u;
             const size_t i = (size_t)t * N + n;
             const float rr = sr[st][u][tid];
@@ -1668,7 +1680,7 @@ __global__ void __launch_bounds__(128) agar_gae_tma_kernel(const float* __restri
             }
         }
         __syncthreads();  // every thread has read stage st: it can be refilled
-        if (tid == 0 && k + STAGES < nb) issue(k + STAGES);
+        if (tid < 32 && k + STAGES < nb) issue(k + STAGES);
     }
 }
 
