@@ -130,6 +130,10 @@ struct AgarEnv {
     StepKernel kernel = nullptr;
     const char* kernel_name = "";
     int64_t launches = 0;
+    // costly-arenas-first launch order (KArgs::order_*): two order buffers of 8 + 4 * N words
+    int32_t* d_order = nullptr;
+    int order_cur = -1;        // which list holds a complete order (-1: none yet)
+    bool order_enabled = true; // AGAR_NO_ORDER (debug switch) read once at create
     // staging for agar_step_host
     float* d_target = nullptr; int32_t* d_act = nullptr; float* d_obs = nullptr;
     float* d_reward = nullptr; uint8_t* d_done = nullptr;
@@ -167,6 +171,18 @@ void note_stream(AgarEnv* e, cudaStream_t st) {
 
 int launch(AgarEnv* e, KArgs& a, int n_records, cudaStream_t st, bool caller_stream = true) {
     a.n_records = n_records;
+    const int N = e->p.c.num_arenas;
+    const bool ordered = e->order_enabled && e->d_order && (a.flags & F_STEP) && !(a.flags & (F_RESET | F_READONLY)) &&
+                         n_records == N && a.arena0 == 0 && N >= 2048;
+    if (ordered) {  // the order written by the last full step launch is consumed by this one, which writes the other buffer
+        const int in = e->order_cur, out = in == 0 ? 1 : 0;
+        const size_t stride = ((size_t)N + 3) / 4 * 4;  // 16-byte aligned lists and headers
+        auto buf = [&](int i) { return e->d_order + (size_t)i * (8 + 4 * stride); };
+        if (in >= 0) a.order_in = buf(in);
+        a.order_out = buf(out);
+        a.order_stride = (int32_t)stride;
+        e->order_cur = out;
+    }
     e->kernel<<<n_records, e->threads, e->smem, st>>>(e->p, a);
     CUDA_OK(cudaGetLastError());
     e->launches += 1;
@@ -357,6 +373,10 @@ static int create_impl(const AgarConfig* cfg, int device, AgarEnv* e, const cuda
         CUDA_OK(cudaMalloc(&e->d_ev_counts, (size_t)cfg->num_arenas * sizeof(int32_t)));
         CUDA_OK(cudaMemsetAsync(e->d_ev_counts, 0, (size_t)cfg->num_arenas * sizeof(int32_t), 0));
     }
+    e->order_enabled = std::getenv("AGAR_NO_ORDER") == nullptr;
+    const size_t order_words = 2 * (8 + 4 * (((size_t)cfg->num_arenas + 3) / 4 * 4));
+    CUDA_OK(cudaMalloc(&e->d_order, order_words * sizeof(int32_t)));
+    CUDA_OK(cudaMemsetAsync(e->d_order, 0, order_words * sizeof(int32_t), 0));
     CUDA_OK(cudaEventCreateWithFlags(&e->order_event, cudaEventDisableTiming));
     // the clears ran on the legacy stream, which non-blocking caller streams do not wait for: finish them here
     CUDA_OK(cudaStreamSynchronize(0));
@@ -387,7 +407,7 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
 int agar_destroy(AgarEnv* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
-    cudaFree(e->d_state); cudaFree(e->d_events); cudaFree(e->d_ev_counts); cudaFree(e->d_hash);
+    cudaFree(e->d_order); cudaFree(e->d_state); cudaFree(e->d_events); cudaFree(e->d_ev_counts); cudaFree(e->d_hash);
     cudaFree(e->d_tab_xy); cudaFree(e->d_tab_act);
     cudaFree(e->d_target); cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_reward); cudaFree(e->d_done);
     if (e->host_stream) cudaStreamDestroy(e->host_stream);

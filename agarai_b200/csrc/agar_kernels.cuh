@@ -75,6 +75,15 @@ struct KArgs {
     int32_t flags;
     int32_t n_records;
     int32_t arena0;          // first arena of this launch (agar_step_host steps the batch in chunks)
+    // Costly arenas first (full-batch step launches only; all null otherwise).  Every CTA measures its own duration and
+    // files its arena into one of four lists of the order written for the next launch, by the ratio to the mean CTA
+    // duration of the previous launch (> 2x, > 1.25x, > 0.85x, rest); the next launch walks the lists from the costliest,
+    // so that the few very costly arenas of an aged batch start in the first round instead of setting the launch's
+    // tail.  An order buffer is {header[8], list[4][order_stride]}; header = {count of class 3, 2, 1, 0, cycle sum
+    // (64 bit), done, 0}.  The last CTA of a launch clears the header of the order it consumed (written next).
+    const int32_t* order_in; // order consumed by this launch, or null (= identity)
+    int32_t* order_out;      // order written by this launch
+    int32_t order_stride;    // capacity of one list (>= N)
 };
 
 enum { F_STEP = 1, F_RESET = 2, F_OBS = 4, F_READONLY = 8 };
@@ -929,7 +938,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     const Smem s = carve(smem_raw, L, G);
     const int tid = threadIdx.x, nt = kThreads, lane = tid & 31;
     const int hbase = lane & 16, slot = lane & 15;
-    const int arena = a.arena0 + blockIdx.x;
+    int arena = a.arena0 + blockIdx.x;
+    if (a.order_in) {  // the lists of the previous launch, costliest class first
+        const int4 cnt = *reinterpret_cast<const int4*>(a.order_in);
+        int b = blockIdx.x, cls = 0;
+        if (b >= cnt.x) { b -= cnt.x; cls = 1; if (b >= cnt.y) { b -= cnt.y; cls = 2; if (b >= cnt.z) { b -= cnt.z; cls = 3; } } }
+        arena = a.order_in[8 + cls * a.order_stride + b];
+    }
+    const long long t_begin = (a.order_out && tid == 0) ? clock64() : 0;
     const int A = CV_INT(A, c.num_agents), K = CV_INT(K, p.K), KC = CV_INT(KC, p.KC), V = CV_INT(V, c.num_viruses), F = CV_INT(F, c.max_foods);
     const uint64_t gid64 = (uint64_t)(c.arena_id_base + arena);
     const uint32_t gid_lo = (uint32_t)gid64, gid_hi = (uint32_t)(gid64 >> 32);
@@ -1524,6 +1540,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     PHASE(15);  // raster
     if (tid == 0) bulk_wait_read0();  // the bulk store must have read the record before the CTA exits
     PHASE(16);  // wait for the bulk store
+    if (a.order_out && tid == 0) {  // file this arena for the next launch
+        const int n = a.n_records;
+        const unsigned long long cyc = (unsigned long long)(clock64() - t_begin);
+        int cls = 3;
+        if (a.order_in) {
+            const unsigned long long mean = *reinterpret_cast<const unsigned long long*>(a.order_in + 4) / (unsigned long long)n;
+            cls = cyc > 2 * mean ? 0 : (cyc > mean + (mean >> 2) ? 1 : (cyc > mean - (mean >> 3) ? 2 : 3));
+        }
+        a.order_out[8 + cls * a.order_stride + atomicAdd(&a.order_out[cls], 1)] = arena;
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.order_out + 4), cyc);
+        __threadfence();
+        if (atomicAdd(&a.order_out[6], 1) == n - 1 && a.order_in) {  // last CTA: the order just consumed is written next
+            int32_t* h = const_cast<int32_t*>(a.order_in);
+            *reinterpret_cast<int4*>(h) = make_int4(0, 0, 0, 0);
+            *reinterpret_cast<int4*>(h + 4) = make_int4(0, 0, 0, 0);
+        }
+    }
     PHASE_FLUSH;
 }
 
