@@ -54,18 +54,23 @@ def build_specialised(cfg, verbose=False):
     names = ("A", "BOTS", "P", "V", "F", "G", "FLAGS", "TICKS")
     # CTAs per SM the shared-memory footprint allows (host-side replica of the bound agar_create computes): the
     # generic launch-bounds ladder 5..8
-    src_hash = hashlib.sha1(b"".join(open(d, "rb").read() for d in DEPS)).hexdigest()[:10]
+    src_hash = hashlib.sha1(b"".join(open(d, "rb").read() for d in DEPS) + " ".join(NVCC_FLAGS).encode()).hexdigest()[:10]
     out_dir = os.path.join(_HERE, "_jit")
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, "libagar_b200_%s_%s.so" % ("_".join(str(k) for k in key), src_hash))
     if os.path.exists(out):
         return out
     blocks = _min_blocks_for(cfg)
+    tmp = "%s.%d.tmp" % (out, os.getpid())  # one process per GPU may build the same key at once: private file, atomic rename
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
         "-DAGAR_EXTRA_CV", "-DAGAR_EXTRA_CV_BLOCKS=%d" % blocks] + ["-DAGAR_EXTRA_%s=%d" % nv for nv in zip(names, key)] + [
-        "-o", out + ".tmp"] + SOURCES
-    subprocess.check_call(cmd)
-    os.replace(out + ".tmp", out)
+        "-o", tmp] + SOURCES
+    try:
+        subprocess.check_call(cmd)
+        os.replace(tmp, out)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return out
 
 

@@ -34,6 +34,16 @@ def gae_and_returns(rewards: torch.Tensor, values: Optional[torch.Tensor], gamma
         raise ValueError("values must be [T+1, N]")
     d = _prep(dones, torch.uint8)
     ev = _prep(end_value, torch.float32)
+    # the kernel (TMA bulk copies included) trusts these shapes: a wrong device or a short buffer would fault the context
+    for name, t in (("values", v), ("dones", d), ("end_value", ev)):
+        if t is not None and t.device != r.device:
+            raise ValueError(f"{name} must live on {r.device} like rewards (got {t.device})")
+    if v is not None and not want_adv and tuple(v.shape) != (T + 1, N):
+        raise ValueError("values must be [T+1, N]")
+    if d is not None and tuple(d.shape) != (T, N):
+        raise ValueError("dones must be [T, N]")
+    if ev is not None and ev.numel() != N:
+        raise ValueError("end_value must hold N elements")
     adv = torch.empty_like(r) if want_adv else None
     ret = torch.empty_like(r) if want_ret else None
     stream = C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
