@@ -691,14 +691,15 @@ int agar_gae(const float* d_reward, const float* d_value, const uint8_t* d_done,
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = (tune_b == 64 || tune_b == 128) ? tune_b : 32, blocks = (N + threads - 1) / threads;
     static const int tune_nb = std::getenv("AGAR_GAE_NB") ? std::atoi(std::getenv("AGAR_GAE_NB")) : 2;
-    // Default: the TMA-fed kernel (ring of 3 shared-memory stages of 8 rows; measured 35-36 us = 61-63 % of the HBM
-    // peak at [128, 65,536] including the launch, against 38-47 us for the register-ring kernel below; 8 rows x 4
-    // stages 37 us, 16 x 2 36 us, 8 x 2 39 us).  It needs whole 128-column strips and 16-byte aligned rows.
+    // Default: the TMA-fed kernel (producer warp + ring of 5 shared-memory stages of 8 rows; measured 30.8 us = 72 % of
+    // the HBM peak at [128, 65,536] including the launch, against 38-47 us for the register-ring kernel below; 3 stages
+    // 31.8 us, 4 stages 31.3 us, 6 stages of 64 columns 31.6 us; profiles/r02_notes.txt).  It needs N % 16 == 0 and
+    // 16-byte aligned rows.
     static const bool no_tma = std::getenv("AGAR_GAE_NO_TMA") != nullptr;
     auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
     if (!no_tma && (N % 16) == 0 && al16(d_reward) && al16(d_value) && al16(d_done)) {
         static const char* tune = std::getenv("AGAR_GAE_TMA");  // tuning switch: "U,STAGES,W"
-        int tu = 8, ts = 3, tw = 128;
+        int tu = 8, ts = 5, tw = 128;
         if (tune) std::sscanf(tune, "%d,%d,%d", &tu, &ts, &tw);
         // strip width: a multiple of 16 columns (bulk copies of the done bytes), at most the CTA's thread count, chosen so
         // that the strips fill per_sm resident CTAs on every SM evenly
@@ -711,9 +712,8 @@ int agar_gae(const float* d_reward, const float* d_value, const uint8_t* d_done,
             if (s0 < 32) s0 = 32;
             return s0 > wmax ? wmax : s0;
         };
-#define GAE_TMA(U_, S_, W_) do { const int strip = strip_for(W_); agar_gae_tma_kernel<U_, S_, W_><<<(N + strip - 1) / strip, W_, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N, strip); } while (0)
+#define GAE_TMA(U_, S_, W_) do { const int strip = strip_for(W_); agar_gae_tma_kernel<U_, S_, W_><<<(N + strip - 1) / strip, W_ + 32, 0, st>>>(d_reward, d_value, d_done, d_end_value, g, cgl, d_adv, d_ret, T, N, strip); } while (0)
         if (tu == 8 && ts == 4 && tw == 128) GAE_TMA(8, 4, 128);
-        else if (tu == 8 && ts == 5 && tw == 128) GAE_TMA(8, 5, 128);
         else if (tu == 10 && ts == 3 && tw == 128) GAE_TMA(10, 3, 128);
         else if (tu == 4 && ts == 6 && tw == 128) GAE_TMA(4, 6, 128);
         else if (tu == 8 && ts == 3 && tw == 64) GAE_TMA(8, 3, 64);
@@ -721,7 +721,8 @@ int agar_gae(const float* d_reward, const float* d_value, const uint8_t* d_done,
         else if (tu == 8 && ts == 2 && tw == 256) GAE_TMA(8, 2, 256);
         else if (tu == 8 && ts == 3 && tw == 32) GAE_TMA(8, 3, 32);
         else if (tu == 8 && ts == 6 && tw == 32) GAE_TMA(8, 6, 32);
-        else GAE_TMA(8, 3, 128);
+        else if (tu == 8 && ts == 3 && tw == 128) GAE_TMA(8, 3, 128);
+        else GAE_TMA(8, 5, 128);
 #undef GAE_TMA
         CUDA_OK(cudaGetLastError());
         return 0;

@@ -1656,82 +1656,94 @@ __global__ void __launch_bounds__(256) agar_gae_kernel(const float* __restrict__
     }
 }
 
-// The same scan fed by TMA: a CTA owns W adjacent columns; warp 0 streams batches of U rows (4W B of r, 4W B
-// of v, W B of done per row, one bulk copy each) into a ring of STAGES shared-memory stages, completion counted on
-// an mbarrier per stage, while the strip's threads scan the stage that has landed.  The strip width is chosen by the host
-// so that the strips fill every SM's resident slots evenly (65,536 columns: 586 strips of 112 on 148 SMs x 4; with
-// fixed 128-column strips the SMs hold 3 or 4 CTAs and the launch lasts as long as the fuller ones).  The bytes in flight no longer live in
-// registers, so the ring can be deep (STAGES x U rows per CTA) without costing occupancy.  Needs N % 128 == 0 and
-// 16-byte aligned buffers (the host falls back to agar_gae_kernel otherwise).
+// The same scan fed by TMA: a CTA owns a strip of adjacent columns.  A producer warp streams batches of U rows (4 B of r,
+// 4 B of v, 1 B of done per column and row, one bulk copy per row and array) into a ring of STAGES shared-memory stages,
+// completion counted on a "full" mbarrier per stage; the W consumer threads scan the stage that has landed, one column
+// each, and every consumer warp releases the stage on its "empty" mbarrier, which the producer waits for before it
+// refills the stage: no CTA-wide barrier, a warp never waits for another consumer warp.  The strip width is chosen by
+// the host so that the strips fill every SM's resident slots evenly (65,536 columns: 586 strips of 112 on 148 SMs x 4;
+// with fixed 128-column strips the SMs hold 3 or 4 CTAs and the launch lasts as long as the fuller ones).  The bytes in
+// flight do not live in registers, so the ring can be deep (STAGES x U rows per CTA) without costing occupancy.  Needs
+// N % 16 == 0 and 16-byte aligned buffers (the host falls back to agar_gae_kernel otherwise).  Block = W + 32 threads.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 template <int U, int STAGES, int W>
-__global__ void __launch_bounds__(W) agar_gae_tma_kernel(const float* __restrict__ r, const float* __restrict__ v,
-                                                          const uint8_t* __restrict__ done,
-                                                          const float* __restrict__ end_value, float g, float cgl,
-                                                          float* __restrict__ adv, float* __restrict__ ret, int T, int N, int strip) {
+__global__ void __launch_bounds__(W + 32) agar_gae_tma_kernel(const float* __restrict__ r, const float* __restrict__ v,
+                                                               const uint8_t* __restrict__ done,
+                                                               const float* __restrict__ end_value, float g, float cgl,
+                                                               float* __restrict__ adv, float* __restrict__ ret, int T, int N, int strip) {
     __shared__ __align__(16) float sr[STAGES][U][W];
     __shared__ __align__(16) float sv[STAGES][U][W];
     __shared__ __align__(16) uint8_t sd[STAGES][U][W];
-    __shared__ __align__(8) uint64_t full[STAGES];
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
     const int tid = threadIdx.x, col0 = blockIdx.x * strip, n = col0 + tid;
     const int width = N - col0 < strip ? N - col0 : strip;  // columns of this strip (a multiple of 16, <= W)
-    const bool active = tid < width;
     const bool want_v = adv != nullptr, want_d = done != nullptr;
     const int nb = (T + U - 1) / U;
-    static_assert(3 * U <= 32, "one lane of warp 0 per (row, array) of a batch");
+    static_assert(3 * U <= 32, "one lane of the producer warp per (row, array) of a batch");
     const int lane = tid & 31;
-    // batch k: rows t = T-1-k*U downwards, at most U of them, into stage k % STAGES.  Called by all of warp 0: lane 0
-    // posts the byte count, then lane 3u+w issues the copy of row u of array w (r, v, done), so a batch costs the warp
-    // a dozen instructions (one thread issuing all 3U copies spent ~250 on address arithmetic, and the other warps
-    // waited for it at the barrier: the kernel was bound by that, profiles/r02_notes.txt).
-    auto issue = [&](int k) {
-        const int st = k % STAGES, t_hi = T - 1 - k * U, rows = t_hi + 1 < U ? t_hi + 1 : U;
-        if (lane == 0) mbar_expect_tx(&full[st], (uint32_t)rows * (uint32_t)width * (4u + (want_v ? 4u : 0u) + (want_d ? 1u : 0u)));
-        __syncwarp();
-        const int u = lane / 3, w = lane - 3 * u;
-        if (u < rows && u < U) {
-            const size_t off = (size_t)(t_hi - u) * N + col0;
-            if (w == 0) bulk_g2s(&sr[st][u][0], r + off, 4u * width, &full[st]);
-            else if (w == 1) { if (want_v) bulk_g2s(&sv[st][u][0], v + off, 4u * width, &full[st]); }
-            else if (want_d) bulk_g2s(&sd[st][u][0], done + off, (uint32_t)width, &full[st]);
-        }
-    };
     if (tid == 0) {
-        for (int st = 0; st < STAGES; ++st) mbar_init(&full[st], 1);
+        for (int st = 0; st < STAGES; ++st) { mbar_init(&full[st], 1); mbar_init(&empty[st], W / 32); }
     }
     __syncthreads();
-    if (tid < 32)
-        for (int k = 0; k < STAGES && k < nb; ++k) issue(k);
+    if (tid >= W) {
+        // ---- producer warp.  Batch k: rows t = T-1-k*U downwards, at most U of them, into stage k % STAGES: lane 0 posts
+        //      the byte count, then lane 3u+w issues the copy of row u of array w (r, v, done) ----
+        for (int k = 0; k < nb; ++k) {
+            const int st = k % STAGES, t_hi = T - 1 - k * U, rows = t_hi + 1 < U ? t_hi + 1 : U;
+            if (k >= STAGES) mbar_wait(&empty[st], (uint32_t)((k / STAGES - 1) & 1));  // the consumers have read batch k - STAGES
+            if (lane == 0) mbar_expect_tx(&full[st], (uint32_t)rows * (uint32_t)width * (4u + (want_v ? 4u : 0u) + (want_d ? 1u : 0u)));
+            __syncwarp();
+            const int u = lane / 3, w = lane - 3 * u;
+            if (u < rows && u < U) {
+                const size_t off = (size_t)(t_hi - u) * N + col0;
+                if (w == 0) bulk_g2s(&sr[st][u][0], r + off, 4u * width, &full[st]);
+                else if (w == 1) { if (want_v) bulk_g2s(&sv[st][u][0], v + off, 4u * width, &full[st]); }
+                else if (want_d) bulk_g2s(&sd[st][u][0], done + off, (uint32_t)width, &full[st]);
+            }
+        }
+        return;
+    }
+    // ---- consumers: one column per thread ----
+    const bool active = tid < width;
     float a_next = 0.0f;
     float g_next = (end_value && active) ? end_value[n] : 0.0f;
     float v_next = (want_v && active) ? __ldcs(v + (size_t)T * N + n) : 0.0f;
+    // one row of the scan; `first` = the row t == T-1 (no successor term)
+    auto row = [&](int st, int u, size_t i, bool first) {
+        const float rr = sr[st][u][tid];
+        const bool cut = want_d && sd[st][u][tid] != 0;
+        if (adv) {
+            const float vv = sv[st][u][tid];
+            const float vn = cut ? 0.0f : v_next;
+            const float delta = (rr + g * vn) - vv;
+            const float av = (first || cut) ? delta : delta + cgl * a_next;
+            __stcs(adv + i, av);
+            a_next = av;
+            v_next = vv;
+        }
+        if (ret) {
+            const float gn = cut ? 0.0f : g_next;
+            const float G_t = rr + g * gn;
+            __stcs(ret + i, G_t);
+            g_next = G_t;
+        }
+    };
     for (int k = 0; k < nb; ++k) {
         const int st = k % STAGES, t_hi = T - 1 - k * U, rows = t_hi + 1 < U ? t_hi + 1 : U;
         mbar_wait(&full[st], (uint32_t)((k / STAGES) & 1));
+        if (active) {
+            size_t i = (size_t)t_hi * N + n;
+            if (rows == U) {  // every batch but possibly the last: no per-row bounds
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (u >= rows || !active) break;
-            const int t = t_hi - u;
-            const size_t i = (size_t)t * N + n;
-            const float rr = sr[st][u][tid];
-            const bool cut = want_d && sd[st][u][tid] != 0;
-            if (adv) {
-                const float vv = sv[st][u][tid];
-                float vn = cut ? 0.0f : v_next;
-                float delta = (rr + g * vn) - vv;
-                float av = (t == T - 1 || cut) ? delta : delta + cgl * a_next;
-                __stcs(adv + i, av);
-                a_next = av;
-                v_next = vv;
-            }
-            if (ret) {
-                float gn = cut ? 0.0f : g_next;
-                float G_t = rr + g * gn;
-                __stcs(ret + i, G_t);
-                g_next = G_t;
+                for (int u = 0; u < U; ++u) { row(st, u, i, u == 0 && k == 0); i -= (size_t)N; }
+            } else {
+                for (int u = 0; u < rows; ++u) { row(st, u, i, u == 0 && k == 0); i -= (size_t)N; }
             }
         }
-        __syncthreads();  // every thread has read stage st: it can be refilled
-        if (tid < 32 && k + STAGES < nb) issue(k + STAGES);
+        __syncwarp();  // the whole warp has read stage st
+        if (lane == 0) mbar_arrive(&empty[st]);
     }
 }
 

@@ -345,7 +345,7 @@ def run_extras(ctx, args, sampler, peak):
     nbytes = T * N * 17 + N * 8
     extras["gae"] = {"config": "BASELINE configs[2]: rl.gae + rl.make_returns over [128, 65536] per GPU, done cut, bootstrap",
                      "us": ms * 1e3, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9,
-                     "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "kernel": "agar_gae_tma_kernel<8,3>",
+                     "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "kernel": "agar_gae_tma_kernel<8,5,128>",
                      "l2": "flushed by a 256 MB write between repetitions", "clocks": sampler.region(t0, time.time()) if ctx.rank == 0 else None}
     del r, v, d, ev
 
