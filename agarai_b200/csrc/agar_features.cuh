@@ -138,8 +138,7 @@ __device__ void ram_nearest_points(unsigned long long* key, unsigned long long* 
                                    const float* ey, int count, bool marker, float lx, float ly, int n, float arena,
                                    float* __restrict__ out) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-    int m = 1;
-    while (m < count) m <<= 1;
+    int m = count > 1 ? 1 << (32 - __clz(count - 1)) : 1;  // next power of two (the bitonic fallback's buffer size)
     if (m > cap) m = cap;
     const bool preselect = count > 64 && n * 2 < count;  // block-uniform
     float rad[RAM_NRAD];
@@ -151,26 +150,45 @@ __device__ void ram_nearest_points(unsigned long long* key, unsigned long long* 
     }
     if (tid < RAM_NRAD + 2) scal[tid] = 0;  // [0..NRAD): entities inside each radius, [NRAD]: compaction cursor, [NRAD+1]: valid entities
     __syncthreads();
-    for (int base = 0; base < m; base += nt) {
-        const int i = base + tid;
-        unsigned long long k = ~0ull;
-        float d = INFINITY;
-        if (i < count) {
-            const float x = ex[i];
-            if (!marker || x >= 0.0f) {
-                const float dx = x - lx, dy = ey[i] - ly;
+    int nval = 0, nin[RAM_NRAD];  // this thread's valid entities, and those inside each radius
+#pragma unroll
+    for (int q = 0; q < RAM_NRAD; ++q) nin[q] = 0;
+    // four entities per thread and pass: the coordinate segments of a record are 16-byte aligned and padded to
+    // multiples of four (padding entries carry x = -1 or lie beyond `count`: masked below)
+    for (int base = 0; base < m; base += 4 * nt) {
+        const int i0 = base + 4 * tid;
+        float xs[4] = {-1.0f, -1.0f, -1.0f, -1.0f}, ys[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (i0 < count) {
+            const float4 x4 = *reinterpret_cast<const float4*>(ex + i0), y4 = *reinterpret_cast<const float4*>(ey + i0);
+            xs[0] = x4.x; xs[1] = x4.y; xs[2] = x4.z; xs[3] = x4.w;
+            ys[0] = y4.x; ys[1] = y4.y; ys[2] = y4.z; ys[3] = y4.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = i0 + e;
+            unsigned long long k = ~0ull;
+            float d = INFINITY;
+            if (i < count && (!marker || xs[e] >= 0.0f)) {
+                const float dx = xs[e] - lx, dy = ys[e] - ly;
                 d = sqrtf(dx * dx + dy * dy);
                 k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
+                ++nval;
+            }
+            if (i < m) key[i] = k;
+            if (preselect) {
+#pragma unroll
+                for (int q = 0; q < RAM_NRAD; ++q) nin[q] += d <= rad[q] ? 1 : 0;
             }
         }
-        if (i < m) key[i] = k;
-        const unsigned vb = __ballot_sync(FULL, k != ~0ull);
-        if (lane == 0 && vb) atomicAdd(&scal[RAM_NRAD + 1], __popc(vb));
+    }
+    {   // one reduction per warp and counter
+        const int tv = __reduce_add_sync(FULL, nval);
+        if (lane == 0 && tv) atomicAdd(&scal[RAM_NRAD + 1], tv);
         if (preselect) {
 #pragma unroll
             for (int q = 0; q < RAM_NRAD; ++q) {
-                const unsigned b = __ballot_sync(FULL, d <= rad[q]);
-                if (lane == 0 && b) atomicAdd(&scal[q], __popc(b));
+                const int tq = __reduce_add_sync(FULL, nin[q]);
+                if (lane == 0 && tq) atomicAdd(&scal[q], tq);
             }
         }
     }
@@ -184,9 +202,15 @@ __device__ void ram_nearest_points(unsigned long long* key, unsigned long long* 
             if (scal[q] >= n && scal[q] <= RAM_CAND_CAP) sel = q;  // smallest sufficient radius
         if (sel >= 0) {  // block-uniform
             const unsigned lim = __float_as_uint(rad[sel]);
-            for (int i = tid; i < m; i += nt) {
-                const unsigned long long k = key[i];
-                if ((unsigned)(k >> 32) <= lim) cand[atomicAdd(&scal[RAM_NRAD], 1)] = k;  // any order: ranks are computed
+            for (int base = 0; base < m; base += nt) {  // warp-uniform; one cursor update per warp
+                const int i = base + tid;
+                const unsigned long long k = i < m ? key[i] : ~0ull;
+                const bool keep = (unsigned)(k >> 32) <= lim;   // (~0ull: distance bits above every radius)
+                const unsigned kb = __ballot_sync(FULL, keep);
+                int pos = 0;
+                if (lane == 0 && kb) pos = atomicAdd(&scal[RAM_NRAD], __popc(kb));
+                pos = __shfl_sync(FULL, pos, 0);
+                if (keep) cand[pos + __popc(kb & ((1u << lane) - 1u))] = k;  // any order: ranks are computed
             }
             __syncthreads();
             keys = cand; C = scal[sel]; nvalid = C;
@@ -294,19 +318,28 @@ __global__ void __launch_bounds__(128) ram_features_kernel(const __grid_constant
     off += 5 * rp.n_cell;
     // closest_players (:186-193): the other players that have cells, by distance between centroids
     // (float32 sqrt(dx*dx + dy*dy)), ties by player index
-    for (int k = warp; k < 64; k += nt >> 5) {
-        unsigned long long kk = ~0ull;
-        if (k < K && k != a) {  // warp-uniform
-            const int g = k * MC + (lane & 15);
-            const bool v = lane < MC;
-            float qx = 0.0f, qy = 0.0f;
-            const bool has = hw_centroid(0, lane & 15, v ? cx[g] : 0.0f, v ? cy[g] : 0.0f, v ? cm[g] : 0.0f, qx, qy);
-            if (has) {
+    for (int k0 = 2 * warp; k0 < 64; k0 += 2 * (nt >> 5)) {  // two players per warp pass, a half-warp each
+        const int hb = lane & 16, sl = lane & 15, k = k0 + (hb >> 4);
+        const bool v = k < K && k != a;
+        const int g = k * MC + sl;
+        const float m = v ? cm[g] : 0.0f, x = v ? cx[g] : 0.0f, y = v ? cy[g] : 0.0f;
+        const int ncell = __popc((__ballot_sync(FULL, m > 0.0f) >> hb) & 0xFFFFu);
+        float qx = 0.0f, qy = 0.0f;
+        if (__any_sync(FULL, ncell >= 2)) {  // warp-uniform: numpy's pairwise order for several cells
+            hw_centroid(hb, sl, x, y, m, qx, qy);
+        } else if (m > 0.0f) {               // np.average over one cell: (x*m)/m, as the general path gives
+            qx = (x * m) / m; qy = (y * m) / m;
+        }
+        // the lane holding a cell (any cell: the centroid is the same in all lanes of the general path) writes the key
+        const unsigned alive = (__ballot_sync(FULL, m > 0.0f) >> hb) & 0xFFFFu;
+        if (sl == (alive ? __ffs(alive) - 1 : 0)) {
+            unsigned long long kk = ~0ull;
+            if (alive) {
                 const float dx = lx - qx, dy = ly - qy;
                 kk = ((unsigned long long)__float_as_uint(sqrtf(dx * dx + dy * dy)) << 32) | (unsigned)k;
             }
+            pkey[k] = kk;
         }
-        if (lane == 0) pkey[k] = kk;
     }
     __syncthreads();
     {   // order the (at most 64) players by counting ranks: sorted[rank] = key, then a barrier
