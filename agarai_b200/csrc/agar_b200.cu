@@ -130,7 +130,7 @@ struct AgarEnv {
     StepKernel kernel = nullptr;
     const char* kernel_name = "";
     int64_t launches = 0;
-    // costly-arenas-first launch order (KArgs::order_*): two order buffers of 8 + 4 * N words
+    // costly-arenas-first launch order (KArgs::order_*): three order buffers of 8 + 4 * N words (read / written / cleared)
     int32_t* d_order = nullptr;
     int order_cur = -1;        // which list holds a complete order (-1: none yet)
     bool order_enabled = true; // AGAR_NO_ORDER (debug switch) read once at create
@@ -174,12 +174,14 @@ int launch(AgarEnv* e, KArgs& a, int n_records, cudaStream_t st, bool caller_str
     const int N = e->p.c.num_arenas;
     const bool ordered = e->order_enabled && e->d_order && (a.flags & F_STEP) && !(a.flags & (F_RESET | F_READONLY)) &&
                          n_records == N && a.arena0 == 0 && N >= 2048;
-    if (ordered) {  // the order written by the last full step launch is consumed by this one, which writes the other buffer
-        const int in = e->order_cur, out = in == 0 ? 1 : 0;
+    if (ordered) {  // the order written by the last full step launch is consumed by this one, which writes the next buffer
+        // and clears the header of the third (the one the launch after this writes; nothing else touches it meanwhile)
+        const int in = e->order_cur, out = in < 0 ? 0 : (in + 1) % 3, clr = (out + 1) % 3;
         const size_t stride = ((size_t)N + 3) / 4 * 4;  // 16-byte aligned lists and headers
         auto buf = [&](int i) { return e->d_order + (size_t)i * (8 + 4 * stride); };
         if (in >= 0) a.order_in = buf(in);
         a.order_out = buf(out);
+        a.order_clear = buf(clr);
         a.order_stride = (int32_t)stride;
         e->order_cur = out;
     }
@@ -374,7 +376,7 @@ static int create_impl(const AgarConfig* cfg, int device, AgarEnv* e, const cuda
         CUDA_OK(cudaMemsetAsync(e->d_ev_counts, 0, (size_t)cfg->num_arenas * sizeof(int32_t), 0));
     }
     e->order_enabled = std::getenv("AGAR_NO_ORDER") == nullptr;
-    const size_t order_words = 2 * (8 + 4 * (((size_t)cfg->num_arenas + 3) / 4 * 4));
+    const size_t order_words = 3 * (8 + 4 * (((size_t)cfg->num_arenas + 3) / 4 * 4));
     CUDA_OK(cudaMalloc(&e->d_order, order_words * sizeof(int32_t)));
     CUDA_OK(cudaMemsetAsync(e->d_order, 0, order_words * sizeof(int32_t), 0));
     CUDA_OK(cudaEventCreateWithFlags(&e->order_event, cudaEventDisableTiming));

@@ -80,9 +80,10 @@ struct KArgs {
     // duration of the previous launch (> 2x, > 1.25x, > 0.85x, rest); the next launch walks the lists from the costliest,
     // so that the few very costly arenas of an aged batch start in the first round instead of setting the launch's
     // tail.  An order buffer is {header[8], list[4][order_stride]}; header = {count of class 3, 2, 1, 0, cycle sum
-    // (64 bit), done, 0}.  The last CTA of a launch clears the header of the order it consumed (written next).
+    // (64 bit), 0, 0}.  Three buffers rotate: block 0 of a launch clears the header of the one the next launch writes.
     const int32_t* order_in; // order consumed by this launch, or null (= identity)
     int32_t* order_out;      // order written by this launch
+    int32_t* order_clear;    // order whose header this launch clears (written by the next launch)
     int32_t order_stride;    // capacity of one list (>= N)
 };
 
@@ -951,6 +952,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         arena = a.order_in[8 + cls * a.order_stride + b];
     }
     const long long t_begin = (a.order_out && tid == 0) ? clock64() : 0;
+    if (a.order_clear && blockIdx.x == 0 && tid == 0) {
+        *reinterpret_cast<int4*>(a.order_clear) = make_int4(0, 0, 0, 0);
+        *reinterpret_cast<int4*>(a.order_clear + 4) = make_int4(0, 0, 0, 0);
+    }
     const int A = CV_INT(A, c.num_agents), K = CV_INT(K, p.K), KC = CV_INT(KC, p.KC), V = CV_INT(V, c.num_viruses), F = CV_INT(F, c.max_foods);
     const uint64_t gid64 = (uint64_t)(c.arena_id_base + arena);
     const uint32_t gid_lo = (uint32_t)gid64, gid_hi = (uint32_t)(gid64 >> 32);
@@ -1547,6 +1552,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
         }
     }
     PHASE(14);  // write back
+    // ---- file this arena for the next launch: class by its duration up to here (the raster costs every arena the same).
+    //      The slot comes back from the atomic while the raster runs; the entry is stored after it ----
+    int order_slot = -1, order_cls = 3;
+    if (a.order_out && tid == 0) {
+        const unsigned long long cyc = (unsigned long long)(clock64() - t_begin);
+        if (a.order_in) {
+            const unsigned long long mean = *reinterpret_cast<const unsigned long long*>(a.order_in + 4) / (unsigned long long)a.n_records;
+            order_cls = cyc > 2 * mean ? 0 : (cyc > mean + (mean >> 2) ? 1 : (cyc > mean - (mean >> 3) ? 2 : 3));
+        }
+        order_slot = atomicAdd(&a.order_out[order_cls], 1);
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.order_out + 4), cyc);
+    }
     // ---- observations ----
     if ((a.flags & F_OBS) && a.obs) {
         __syncthreads();
@@ -1558,23 +1575,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     PHASE(15);  // raster
     if (tid == 0) bulk_wait_read0();  // the bulk store must have read the record before the CTA exits
     PHASE(16);  // wait for the bulk store
-    if (a.order_out && tid == 0) {  // file this arena for the next launch
-        const int n = a.n_records;
-        const unsigned long long cyc = (unsigned long long)(clock64() - t_begin);
-        int cls = 3;
-        if (a.order_in) {
-            const unsigned long long mean = *reinterpret_cast<const unsigned long long*>(a.order_in + 4) / (unsigned long long)n;
-            cls = cyc > 2 * mean ? 0 : (cyc > mean + (mean >> 2) ? 1 : (cyc > mean - (mean >> 3) ? 2 : 3));
-        }
-        a.order_out[8 + cls * a.order_stride + atomicAdd(&a.order_out[cls], 1)] = arena;
-        atomicAdd(reinterpret_cast<unsigned long long*>(a.order_out + 4), cyc);
-        __threadfence();
-        if (atomicAdd(&a.order_out[6], 1) == n - 1 && a.order_in) {  // last CTA: the order just consumed is written next
-            int32_t* h = const_cast<int32_t*>(a.order_in);
-            *reinterpret_cast<int4*>(h) = make_int4(0, 0, 0, 0);
-            *reinterpret_cast<int4*>(h + 4) = make_int4(0, 0, 0, 0);
-        }
-    }
+    if (order_slot >= 0) a.order_out[8 + order_cls * a.order_stride + order_slot] = arena;
     PHASE_FLUSH;
 }
 
