@@ -323,6 +323,23 @@ def run_extras(ctx, args, sampler, peak):
     n4 = CFG4_ARENAS_PER_GPU if free > 80e9 else 4096
     extras["cfg4_world"] = world_entry("cfg4", n4, min(args.age, 200), "BASELINE configs[3] world: " + describe(WORLDS["cfg4"]))
 
+    # configs[4]: env-step throughput sweep over the arena count (cfg1 world; per GPU 1 Ki .. 512 Ki arenas, i.e. 1 K .. 4 M arenas
+    # over 1 .. 8 GPUs), device-resident with the grid observation, each size aged by 200 untimed steps
+    sweep = []
+    for n_sw in (1024, 4096, 16384, 65536, 262144, 524288):
+        free, _ = torch.cuda.mem_get_info(ctx.dev)
+        if free < 2.5 * n_sw * 49152 + 2e9:  # two observation buffers + state
+            continue
+        r = time_world(ctx, "cfg1", n_sw, 20, W, 200, args.seed)
+        B, gbs, frac = roofline_of(r["world"], n_sw, r["ms_per_launch"], peak)
+        sweep.append({"arenas_per_gpu": n_sw, "arenas_total": ctx.world * n_sw, "us": r["ms_per_launch"] * 1e3,
+                      "env_steps_per_s": ctx.world * n_sw / (r["ms_per_launch"] * 1e-3), "frac": frac})
+        r["env"].close()
+        del r
+        torch.cuda.empty_cache()
+    extras["sweep_cfg1_world"] = {"config": "BASELINE configs[4]: " + describe(WORLDS["cfg1"]) + ", episode age 200, 20 timed steps per size",
+                                  "points": sweep}
+
     # rl.gae + rl.make_returns at configs[2]: T=128, N=65,536, gamma .75, lambda .1 (17 B per (t, n): SURVEY.md §8d)
     T, N = 128, 65536
     dev = ctx.dev
