@@ -143,7 +143,7 @@ __device__ void ram_nearest_points(unsigned long long* key, unsigned long long* 
     const bool preselect = count > 64 && n * 2 < count;  // block-uniform
     float rad[RAM_NRAD];
     {
-        const float r0 = sqrtf((float)n * arena * arena / (3.14159265f * (float)(count > 0 ? count : 1)));
+        const float r0 = preselect ? sqrtf((float)n * arena * arena / (3.14159265f * (float)count)) : 0.0f;
         const float mult[RAM_NRAD] = {1.25f, 1.5f, 1.8f, 2.2f, 3.0f, 4.5f, 7.0f};
 #pragma unroll
         for (int q = 0; q < RAM_NRAD; ++q) rad[q] = r0 * mult[q];
@@ -246,6 +246,15 @@ __device__ void ram_player_cells(const float* cx, const float* cy, const float* 
     const float m = in ? cm[lane] : 0.0f;
     const float x = in ? cx[lane] : 0.0f, y = in ? cy[lane] : 0.0f;
     const bool alive = m > 0.0f;
+    const unsigned aliveb = __ballot_sync(FULL, alive);
+    if (__popc(aliveb) <= 1) {  // the usual player: one cell (or none), nothing to rank
+        if (alive && n > 0) {
+            out[0] = relative ? x - lx : x; out[1] = relative ? y - ly : y;
+            out[2] = cix[lane]; out[3] = ciy[lane]; out[4] = m;
+        }
+        for (int r = (aliveb && n > 0 ? 5 : 0) + lane; r < n * 5; r += 32) out[r] = 0.0f;
+        return;
+    }
     // rank by (mass, slot) among alive cells
     int rank_m = 0;
     for (int j = 0; j < MC; ++j) {
@@ -348,7 +357,7 @@ __global__ void __launch_bounds__(128) ram_features_kernel(const __grid_constant
         if (tid < 64) {
             mine = pkey[tid];
             rank = 0;
-            for (int j = 0; j < 64; ++j) rank += pkey[j] < mine ? 1 : 0;
+            for (int j = 0; j < K; ++j) rank += pkey[j] < mine ? 1 : 0;  // (entries from K on are ~0ull)
         }
         __syncthreads();
         if (tid < 64) pkey[tid] = ~0ull;

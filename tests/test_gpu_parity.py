@@ -345,6 +345,43 @@ def test_large_batch_properties(oracle):
     env.close()
 
 
+def test_costly_arenas_first_order_does_not_change_results(monkeypatch):
+    """Full-batch step launches of >= 2048 arenas map blocks to arenas through the cost-class lists the previous launch
+    filed (three rotating order buffers).  The order is scheduling only: a twin env with the order switched off
+    (AGAR_NO_ORDER, read at create) must stay bit-identical in state, observations, rewards and dones, including across a
+    masked reset and a host-buffer step in between (which do not use the lists)."""
+    import agarai_b200 as ab
+    kw = dict(num_arenas=2304, num_agents=1, num_bots=6, num_viruses=4, num_pellets=200, arena_size=150.0, grid_size=16,
+              obs_flags=7, auto_reset=1, start_mass=30.0, virus_pop_mass=60.0, virus_mass=30.0)
+    a = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=5, action_config=ab.ActionConfig(8, 1, True, True))
+    monkeypatch.setenv("AGAR_NO_ORDER", "1")
+    b = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=5, action_config=ab.ActionConfig(8, 1, True, True))
+    monkeypatch.delenv("AGAR_NO_ORDER")
+    assert torch.equal(a.reset(), b.reset())
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    N = kw["num_arenas"]
+    for t in range(40):
+        idx = torch.randint(0, a.num_actions, (N, 1), generator=g, device="cuda", dtype=torch.int32)
+        oa, ra, da, _ = a.step_discrete(idx)
+        ob, rb, db, _ = b.step_discrete(idx)
+        assert torch.equal(oa.view(torch.int32), ob.view(torch.int32)), t
+        assert torch.equal(ra.view(torch.int32), rb.view(torch.int32)) and torch.equal(da, db), t
+        if t == 15:  # a masked reset between ordered launches
+            mask = (torch.arange(N, device="cuda") % 3 == 0).to(torch.uint8)
+            assert torch.equal(a.reset(mask), b.reset(mask))
+        if t == 25:  # a chunked host-buffer step (sub-batch launches: no lists) between ordered launches
+            xy = np.zeros((N, 1, 2), f32); xy[:, 0, 0] = 0.7
+            act = np.zeros((N, 1), np.int32)
+            outs = []
+            for e in (a, b):
+                ho = np.empty(tuple(e.obs_shape), f32); hr = np.empty((N, 1), f32); hd = np.empty((N, 1), np.uint8)
+                e.step_host(xy, act, ho, hr, hd)
+                outs.append((ho, hr, hd))
+            assert all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(*outs))
+    assert torch.equal(a.get_state().view(torch.int32), b.get_state().view(torch.int32))
+    a.close(); b.close()
+
+
 def test_ppo_loop_runs_and_snapshots_rerasterise_exactly(oracle):
     """configs[2] shape at test size: rollout with GAE on the GPU, SGD on minibatches whose
     observations are re-rasterised from state snapshots (keep="state"); the re-rasterised observations equal the
