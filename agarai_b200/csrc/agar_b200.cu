@@ -172,8 +172,13 @@ void note_stream(AgarEnv* e, cudaStream_t st) {
 int launch(AgarEnv* e, KArgs& a, int n_records, cudaStream_t st, bool caller_stream = true) {
     a.n_records = n_records;
     const int N = e->p.c.num_arenas;
-    const bool ordered = e->order_enabled && e->d_order && (a.flags & F_STEP) && !(a.flags & (F_RESET | F_READONLY)) &&
-                         n_records == N && a.arena0 == 0 && N >= 2048;
+    bool ordered = e->order_enabled && e->d_order && (a.flags & F_STEP) && !(a.flags & (F_RESET | F_READONLY)) &&
+                   n_records == N && a.arena0 == 0 && N >= 2048;
+    if (ordered) {  // the order buffers rotate from launch to launch: a launch captured into a CUDA graph would replay with
+        // one fixed triple (its output list never cleared), so captured launches keep the identity order
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { ordered = false; (void)cudaGetLastError(); }
+    }
     if (ordered) {  // the order written by the last full step launch is consumed by this one, which writes the next buffer
         // and clears the header of the third (the one the launch after this writes; nothing else touches it meanwhile)
         const int in = e->order_cur, out = in < 0 ? 0 : (in + 1) % 3, clr = (out + 1) % 3;

@@ -1575,7 +1575,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
     PHASE(15);  // raster
     if (tid == 0) bulk_wait_read0();  // the bulk store must have read the record before the CTA exits
     PHASE(16);  // wait for the bulk store
-    if (order_slot >= 0) a.order_out[8 + order_cls * a.order_stride + order_slot] = arena;
+    if (order_slot >= 0 && order_slot < a.order_stride) a.order_out[8 + order_cls * a.order_stride + order_slot] = arena;
     PHASE_FLUSH;
 }
 

@@ -382,6 +382,39 @@ def test_costly_arenas_first_order_does_not_change_results(monkeypatch):
     a.close(); b.close()
 
 
+def test_step_captured_in_a_cuda_graph_replays_like_plain_steps():
+    """A step launch captured into a CUDA graph and replayed (launch-bound inner loops) gives the results of plain
+    launches: the launch-order buffers rotate on the host side from launch to launch, so a captured launch must not use
+    them (it would replay one fixed triple of buffers)."""
+    import agarai_b200 as ab
+    kw = dict(num_arenas=2304, num_agents=1, num_bots=5, num_viruses=3, num_pellets=200, arena_size=150.0, grid_size=16,
+              obs_flags=7, auto_reset=1, start_mass=30.0)
+    a = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=8, action_config=ab.ActionConfig(8, 1, True, True))
+    b = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=8, action_config=ab.ActionConfig(8, 1, True, True))
+    assert torch.equal(a.reset(), b.reset())
+    N = kw["num_arenas"]
+    gen = torch.Generator(device="cuda"); gen.manual_seed(4)
+    idx_all = torch.randint(0, a.num_actions, (12, N, 1), generator=gen, device="cuda", dtype=torch.int32)
+    for t in range(3):  # a few plain (ordered) launches first: an order is pending when the capture starts
+        a.step_discrete(idx_all[t]); b.step_discrete(idx_all[t])
+    idx = idx_all[3].clone()
+    obs = torch.empty(a.obs_shape, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        _, rew, done, _ = a.step_discrete(idx, out_obs=obs)
+    for t in range(3, 12):
+        idx.copy_(idx_all[t])
+        graph.replay()
+        ob, rb, db, _ = b.step_discrete(idx_all[t])
+        torch.cuda.synchronize()
+        assert torch.equal(obs.view(torch.int32), ob.view(torch.int32)), t
+        assert torch.equal(rew.view(torch.int32), rb.view(torch.int32)) and torch.equal(done, db), t
+    assert torch.equal(a.get_state().view(torch.int32), b.get_state().view(torch.int32))
+    a.close(); b.close()
+
+
 def test_ppo_loop_runs_and_snapshots_rerasterise_exactly(oracle):
     """configs[2] shape at test size: rollout with GAE on the GPU, SGD on minibatches whose
     observations are re-rasterised from state snapshots (keep="state"); the re-rasterised observations equal the
