@@ -249,10 +249,10 @@ def test_gae_matches_oracle_and_reference_golden(oracle):
         assert np.array_equal(adv.cpu().numpy()[:, 0], z["adv"][:, n])
         assert np.array_equal(ret.cpu().numpy()[:, 0], z["ret0"][:, n])
     rng = np.random.default_rng(8)
-    # N % 128 == 0 takes the TMA-fed kernel (ring of 8-row stages: T below, at and across the stage and ring sizes);
-    # other widths the register-ring kernel
+    # N % 16 == 0 takes the TMA-fed kernel (producer warp, ring of five 8-row stages: T below, at and across the stage
+    # and ring sizes, strips narrower than a CTA and a ragged last strip); other widths the register-ring kernel
     for T, N in ((1, 1), (3, 5), (128, 1000), (513, 257), (7, 4099), (1, 128), (8, 256), (9, 128), (24, 384), (25, 128),
-                 (128, 65536), (131, 1280)):
+                 (128, 65536), (131, 1280), (41, 48), (40, 176), (81, 2064), (200, 112), (39, 75776 + 16)):
         rr = rng.normal(size=(T, N)).astype(f32); vv = rng.normal(size=(T + 1, N)).astype(f32)
         dd = (rng.random((T, N)) < 0.05).astype(np.uint8); ev = rng.normal(size=N).astype(f32)
         for done, end in ((None, None), (dd, ev)):
