@@ -781,8 +781,7 @@ int agar_screen_gray(const uint8_t* d_rgb, int64_t n_pixels, void* d_out, int32_
     if (n_pixels == 0) return 0;
     if (!d_rgb || !d_out) return fail("NULL argument");
     if (((uintptr_t)d_rgb & 15) != 0 || ((uintptr_t)d_out & 15) != 0) return fail("agar_screen_gray: buffers must be 16-byte aligned");
-    const long long threads = (n_pixels + 15) / 16;
-    const unsigned blocks = (unsigned)((threads + 255) / 256);
+    const unsigned blocks = (unsigned)((n_pixels + GRAY_TILE - 1) / GRAY_TILE);  // a CTA per tile of 4096 pixels
     if (out_f64) screen_gray_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_rgb, (long long)n_pixels, (double*)d_out);
     else screen_gray_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_rgb, (long long)n_pixels, (float*)d_out);
     CUDA_OK(cudaGetLastError());

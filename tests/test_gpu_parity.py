@@ -618,6 +618,10 @@ def test_screen_gray_matches_reference_golden(oracle):
     got = ex.extract(big)
     assert np.array_equal(got.cpu().numpy(), big.cpu().numpy().mean(axis=-1))  # numpy's own statement, full size
     assert np.array_equal(got[:2].cpu().numpy(), oracle.screen_gray(big[:2].cpu().numpy()))
+    assert np.array_equal(ex.extract(big, dtype=torch.float32).cpu().numpy(), big.cpu().numpy().mean(axis=-1).astype(np.float32))
+    ragged = big.reshape(-1, 3)[:3 * 4096 + 100].reshape(1, -1, 3).contiguous()   # three whole tiles and a partial one
+    for dt, npdt in ((torch.float64, np.float64), (torch.float32, np.float32)):
+        assert np.array_equal(ex.extract(ragged, dtype=dt).cpu().numpy(), ragged.cpu().numpy().mean(axis=-1).astype(npdt))
     assert ex.extract(big[:0]).shape == (0, 4, 128, 128)
 
 
