@@ -71,6 +71,14 @@ def build_specialised(cfg, verbose=False):
     finally:
         if os.path.exists(tmp):
             os.remove(tmp)
+    # builds of the same size tuple from older sources (another hash) are dead weight: drop them
+    prefix = "libagar_b200_%s_" % "_".join(str(k) for k in key)
+    for name in os.listdir(out_dir):
+        if name.startswith(prefix) and name.endswith(".so") and os.path.join(out_dir, name) != out:
+            try:
+                os.remove(os.path.join(out_dir, name))
+            except OSError:
+                pass
     return out
 
 
