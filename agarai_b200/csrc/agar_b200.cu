@@ -769,6 +769,7 @@ int agar_observe_ram(AgarEnv* e, int32_t n_pellet, int32_t n_virus, int32_t n_fo
     while (rp.sort_cap < most) rp.sort_cap <<= 1;
     const size_t smem = (size_t)(rp.sort_cap + 64 + RAM_CAND_CAP) * sizeof(unsigned long long);
     CUDA_OK(cudaFuncSetAttribute(ram_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(ram_features_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ram_features_kernel<<<c.num_arenas * c.num_agents, 128, smem, (cudaStream_t)stream>>>(e->p, rp, e->d_state, d_out);
     CUDA_OK(cudaGetLastError());
     e->launches += 1;

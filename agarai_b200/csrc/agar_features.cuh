@@ -303,7 +303,10 @@ __device__ void ram_player_cells(const float* cx, const float* cy, const float* 
 }
 
 // grid = (arenas * agents); block = 128; dynamic smem = (sort_cap + 64 + RAM_CAND_CAP) * 8 bytes.
-__global__ void __launch_bounds__(128) ram_features_kernel(const __grid_constant__ DevParams p, const __grid_constant__ RamParams rp,
+#ifndef RAM_MIN_BLOCKS
+#define RAM_MIN_BLOCKS 10  // 51 registers: 10 CTAs per SM = 2.8 rounds for 4096 agents (9 CTAs: a fourth, nearly empty round)
+#endif
+__global__ void __launch_bounds__(128, RAM_MIN_BLOCKS) ram_features_kernel(const __grid_constant__ DevParams p, const __grid_constant__ RamParams rp,
                                                            const float* __restrict__ state, float* __restrict__ out_all) {
     extern __shared__ __align__(16) unsigned long long ram_smem[];
     unsigned long long* key = ram_smem;              // [sort_cap]
