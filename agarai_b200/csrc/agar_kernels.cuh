@@ -1228,10 +1228,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) agar_step_kernel(const _
                 for (int qb = (tid >> 5) * 8; qb < n; qb += nt >> 2) {  // 8 cells per warp pass, warp-uniform
                     const int q = qb + (lane >> 2);
                     const int g = q < n ? s.list[q] : s.list[0];
-                    const float m = q < n ? cm[g] : 0.0f;
+                    float m = q < n ? cm[g] : 0.0f;
                     const float ox = cx[g], oy = cy[g], oix = cix[g], oiy = ciy[g], t = ct[g];
                     __syncwarp();  // lane 0 of a quad stores the cell below: its whole quad has read it by now
                     if (!(m > 0.0f)) continue;  // no cell, or it died earlier in this step
+                    if (c.mass_decay > 0.0f) {  // mass decay (own-spec rule, off by default): never below start_mass
+                        const float md = m * (1.0f - c.mass_decay);
+                        if (md >= c.start_mass) { m = md; if (l4 == 0) cm[g] = m; }
+                    }
                     const int k = g >> 4;
                     const float r2 = m * r2pm;
                     const float r = sqrtf(r2);

@@ -57,6 +57,9 @@ WORLDS = {
                      grid_size=32, obs_flags=15, pellet_regen=1, auto_reset=1, max_foods=64),
     "dqn": dict(num_agents=1, num_bots=0, num_viruses=0, num_pellets=30, arena_size=45.0, ticks_per_step=4,
                 grid_size=128, obs_flags=15, pellet_regen=1, auto_reset=1, max_foods=64, view_size=30.0),
+    # the headline world with the optional mass-decay rule on (AgarConfig.mass_decay; 2e-4 per tick = 2 % per second at 25 steps/s)
+    "cfg2_decay": dict(num_agents=1, num_bots=25, num_viruses=25, num_pellets=1000, arena_size=500.0, ticks_per_step=4,
+                       grid_size=64, obs_flags=7, pellet_regen=1, auto_reset=1, max_foods=64, mass_decay=2e-4),
 }
 WORLD = WORLDS["cfg2"]
 METRIC = "env_steps_per_sec_incl_grid_obs"
@@ -96,7 +99,8 @@ def measured_peak_gbs():
 
 def describe(w):
     return (f"{w['num_agents']} agent(s) + {w['num_bots']} bots + {w['num_viruses']} viruses, {w['num_pellets']} pellets, "
-            f"arena {w['arena_size']:g}, obs {bin(w['obs_flags']).count('1')}x{w['grid_size']}x{w['grid_size']} f32 per agent")
+            f"arena {w['arena_size']:g}, obs {bin(w['obs_flags']).count('1')}x{w['grid_size']}x{w['grid_size']} f32 per agent"
+            + (f", mass_decay {w['mass_decay']:g} per tick" if w.get("mass_decay") else ""))
 
 
 class ClockSampler:
@@ -318,6 +322,7 @@ def run_extras(ctx, args, sampler, peak):
         return e
 
     extras["cfg1_world"] = world_entry("cfg1", args.arenas, args.age, "BASELINE configs[0]/[2]/[4] world: " + describe(WORLDS["cfg1"]))
+    extras["cfg2_mass_decay"] = world_entry("cfg2_decay", args.arenas, args.age, "headline world with the optional mass-decay rule: " + describe(WORLDS["cfg2_decay"]))
     # configs[3]: 262,144 arenas over 8 GPUs = 32,768 per GPU (25.8 GB of observations per step and GPU)
     free, _ = torch.cuda.mem_get_info(ctx.dev)
     n4 = CFG4_ARENAS_PER_GPU if free > 80e9 else 4096
@@ -542,7 +547,7 @@ def main():
     WORLD = dict(WORLDS[args.world])
     for kv in args.set:
         k, v = kv.split("=")
-        WORLD[k] = type(WORLDS[args.world].get(k, 0))(float(v))
+        WORLD[k] = type(WORLDS[args.world][k])(float(v)) if k in WORLDS[args.world] else (float(v) if any(ch in v for ch in ".e") else int(v))
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -132,7 +132,8 @@ typedef struct AgarConfig {
     /* bots */
     int32_t bot_roam_period; /* ticks between roam way-points (power of two)             */
     float bot_sense_radius;  /* bots chase the nearest pellet within this square window  */
-    float reserved1;
+    float mass_decay;        /* fraction of its mass a cell loses per tick while the rest stays >=
+                                start_mass (applied at the start of the tick's motion); 0 = off */
 } AgarConfig;
 
 /* Offsets (in 32-bit words) of each field inside one arena's state record.  The world

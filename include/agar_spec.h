@@ -82,6 +82,7 @@ static inline const char* agar_spec_config_check(const AgarConfig* c) {
     if (c->pop_pieces < 0 || c->pop_pieces > 15) return "pop_pieces must be in [0, 15]";
     if (c->bot_roam_period < 1 || (c->bot_roam_period & (c->bot_roam_period - 1)))
         return "bot_roam_period must be a power of two";
+    if (!(c->mass_decay >= 0.0f && c->mass_decay < 0.5f)) return "mass_decay must be in [0, 0.5)";
     if (c->event_capacity < 0 || c->event_capacity > 65536) return "event_capacity out of range";
     return 0;
 }

@@ -411,6 +411,10 @@ static void step_arena(OracleEnv* e, int n, const float* target_xy, const int32_
         for (int g = 0; g < KC; ++g) {
             float m = cm[g];
             if (!(m > 0.0f)) continue;
+            if (c->mass_decay > 0.0f) { /* mass decay: the cell keeps (1 - mass_decay) of its mass, never below start_mass */
+                float md = m * (1.0f - c->mass_decay);
+                if (md >= c->start_mass) { m = md; cm[g] = m; }
+            }
             int k = g / MC;
             float r = sqrtf(m * r2pm);
             float spd = c->speed_k / sqrtf(r);

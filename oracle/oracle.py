@@ -29,7 +29,7 @@ class AgarConfig(C.Structure):
         ("target_reach", C.c_float), ("split_speed", C.c_float), ("impulse_decay", C.c_float),
         ("feed_speed", C.c_float), ("food_decay", C.c_float), ("food_spawn_gap", C.c_float),
         ("pop_speed", C.c_float), ("merge_delay", C.c_float), ("pop_pieces", C.c_int32),
-        ("bot_roam_period", C.c_int32), ("bot_sense_radius", C.c_float), ("reserved1", C.c_float),
+        ("bot_roam_period", C.c_int32), ("bot_sense_radius", C.c_float), ("mass_decay", C.c_float),
     ]
 
 

@@ -28,7 +28,7 @@ def random_config(rng):
         merge_delay=float(rng.choice([0.0, 3.0, 12.0, 400.0])), virus_mass=float(rng.choice([30.0, 100.0])),
         virus_pop_mass=float(rng.choice([35.0, 60.0, 110.0])), speed_k=float(rng.choice([1.0, 3.0, 8.0])),
         pop_pieces=int(rng.choice([0, 3, 7, 15])), split_min_mass=float(rng.choice([12.0, 20.0])), bot_sense_radius=float(rng.choice([8.0, 64.0, 500.0])),
-        arena_id_base=int(rng.choice([0, 7, 2 ** 33])))
+        arena_id_base=int(rng.choice([0, 7, 2 ** 33])), mass_decay=float(rng.choice([0.0, 0.0, 0.0005, 0.02])))
     if kw["max_foods"] == 0:
         kw["max_foods"] = 1
     return kw

@@ -798,6 +798,40 @@ def test_crowded_arena_eat_test(oracle):
     genv.close()
 
 
+def test_mass_decay_rule_matches_oracle(oracle):
+    """AgarConfig.mass_decay (own-spec rule, off by default): every alive cell loses that fraction of its mass at the
+    start of a tick's motion unless the rest would fall below start_mass.  cfg2 world (the compile-time specialised
+    kernel) and a dense world where every rule fires, both with a strong decay so that it shapes the trajectory."""
+    import agarai_b200 as ab
+    import bench
+    n, seed = 6, 21
+    kw = dict(bench.WORLDS["cfg2"], num_arenas=n, mass_decay=0.002)
+    genv = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=seed, action_config=ab.ActionConfig(8, 1, True, True))
+    assert genv.kernel_variant == "cfg2"
+    oenv = oracle.OracleEnv(oracle.default_config(**kw), seed=seed, nthreads=8)
+    xy_tab, act_tab = ab.ppo_action_table(ab.ActionConfig(8, 1, True, True))
+    assert np.array_equal(genv.reset().cpu().numpy(), oenv.reset())
+    rng = np.random.default_rng(seed)
+    L = genv.layout
+    for t in range(400):
+        idx = rng.integers(0, len(act_tab), (n, 1))
+        go, gr, gd, _ = genv.step_discrete(torch.from_numpy(idx.astype(np.int32)).cuda())
+        oo, orr, od = oenv.step(xy_tab[idx], act_tab[idx])
+        assert np.array_equal(genv.get_state().cpu().numpy().view(np.int32), oenv.get_state().view(np.int32)), f"state, step {t}"
+        assert np.array_equal(go.cpu().numpy().view(np.int32), oo.view(np.int32)), f"obs, step {t}"
+        assert np.array_equal(gr.cpu().numpy().view(np.int32), orr.view(np.int32)) and np.array_equal(gd.cpu().numpy(), od), f"step {t}"
+    m = genv.get_state().cpu().numpy()[:, L.cell_m:L.cell_m + L.cells_total]
+    assert (m[m > 0] >= 10.0).all()  # never below start_mass
+    genv.close(); oenv.close()
+    genv, oenv = make_pair(oracle, seed=3, num_arenas=8, num_agents=4, num_bots=6, num_viruses=6, num_pellets=400,
+                           max_foods=16, arena_size=120.0, view_size=100.0, grid_size=32, obs_flags=31,
+                           event_capacity=1024, auto_reset=1, start_mass=40.0, merge_delay=12.0,
+                           virus_mass=30.0, virus_pop_mass=60.0, speed_k=6.0, pop_pieces=5, mass_decay=0.01)
+    counts = lockstep(genv, oenv, 300, np.random.default_rng(2), p_act=0.5)
+    assert counts[4] > 0 and counts[6] > 0, counts
+    genv.close()
+
+
 def test_aged_cfg2_world_lockstep(oracle):
     """The regime a training run lives in (bench.py `episode_age_steps`): the BASELINE configs[1] world stepped for 1,500
     steps with the bench's random policy, state / observations / rewards / dones compared with the oracle at every step.

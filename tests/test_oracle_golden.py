@@ -177,6 +177,32 @@ def test_env_multithreaded_step_is_identical(oracle):
     assert np.array_equal(a.get_state().view(np.int32), b.get_state().view(np.int32))
 
 
+def test_env_mass_decay_rule(oracle):
+    """AgarConfig.mass_decay (own-spec rule; 0 = off is the default and leaves every trace unchanged): a lone cell that
+    eats nothing keeps (1 - d) of its mass per tick in float32, and stops once the next product would fall below
+    start_mass."""
+    assert oracle.default_config().mass_decay == 0.0
+    f32 = np.float32
+    cfg = oracle.default_config(num_arenas=1, num_pellets=0, ticks_per_step=4, mass_decay=0.01, auto_reset=0)
+    env = oracle.OracleEnv(cfg, seed=1); env.reset()
+    L = env.L
+    st = env.get_state(); st[0, L.cell_m] = 50.0; env.set_state(st)
+    m, keep = f32(50.0), f32(1.0) - f32(0.01)
+    for t in range(60):
+        _, rew, _ = env.step(np.zeros((1, 1, 2), f32), np.zeros((1, 1), np.int32))
+        m0 = m
+        for _ in range(4):
+            md = f32(m * keep)
+            if md >= f32(10.0):
+                m = md
+        got = env.get_state()[0, L.cell_m]
+        assert got.view(np.int32) == m.view(np.int32), (t, got, m)
+        assert rew[0, 0] == f32(m - m0)
+    assert f32(10.0) <= m < f32(10.2)
+    with pytest.raises(ValueError):
+        oracle.OracleEnv(oracle.default_config(mass_decay=0.7))
+
+
 # ---------------------------------------------------------------- RAM-style / screen extractors
 def load_ram_cases():
     z = np.load(os.path.join(GOLD, "ram_golden.npz"))
