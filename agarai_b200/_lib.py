@@ -60,6 +60,7 @@ SYMBOLS = [
     ("agar_set_state", C.c_int, [_P, _P, _P]),
     ("agar_events", C.c_int, [_P, _P, _P, _P]),
     ("agar_step_host", C.c_int, [_P, _P, _P, _P, _P, _P]),
+    ("agar_host_obs_persistent", C.c_int, [_P, C.c_int]),
     ("agar_gae", C.c_int, [_P, _P, _P, _P, C.c_double, C.c_double, _P, _P, C.c_int32, C.c_int32, _P]),
     ("agar_ram_feature_size", C.c_int, [C.c_int32] * 5),
     ("agar_observe_ram", C.c_int, [_P] + [C.c_int32] * 5 + [_P, _P]),

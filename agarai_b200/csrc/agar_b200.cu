@@ -5,8 +5,10 @@
 #include <immintrin.h>
 #include <sched.h>
 
+#include <atomic>
 #include <cmath>
 #include <condition_variable>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -66,8 +68,7 @@ bool matches(const AgarConfig& c, const AgarLayout& L) {
            L.agent_done == SL::agent_done && L.tick == SL::tick && L.dyn_begin == SL::dyn_begin;
 }
 
-// Host worker threads of agar_step_host's compact copy: run(fn) calls fn(worker, workers) on every worker and returns
-// when all of them are done.
+// Host worker threads of agar_step_host's compact copy: fn(worker, workers) runs on every worker.
 class HostPool {
 public:
     explicit HostPool(int n) : n_(n) {
@@ -78,10 +79,14 @@ public:
         cv_.notify_all();
         for (auto& t : th_) t.join();
     }
-    void run(const std::function<void(int, int)>& fn) {
-        std::unique_lock<std::mutex> lk(m_);
+    // start(fn) hands fn to every worker and returns; wait() returns when all of them are done (fn must live until then)
+    void start(const std::function<void(int, int)>& fn) {
+        std::lock_guard<std::mutex> lk(m_);
         job_ = &fn; ++gen_; pending_ = n_;
         cv_.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m_);
         done_.wait(lk, [&] { return pending_ == 0; });
     }
 
@@ -149,7 +154,16 @@ struct AgarEnv {
     bool host_compact = false;
     int entry_cap = 0;
     ObsEntry* d_entries = nullptr; int32_t* d_counts = nullptr; float* d_meta = nullptr;
-    ObsEntry* h_entries = nullptr; int32_t* h_counts = nullptr; float* h_meta = nullptr;  // pinned
+    ObsEntry* h_entries = nullptr; int32_t* h_counts = nullptr; float* h_meta = nullptr;  // pinned, two halves: this step's / the previous step's
+    // persistent host observation buffer (agar_host_obs_persistent): the previous step's lists describe what h_obs holds
+    bool host_persistent = false;
+    int hbuf = 0;                      // which half of h_entries / h_counts / h_meta the last completed call filled
+    const float* delivered = nullptr;  // h_obs of the last completed compact call (nullptr: contents unknown)
+    // AGAR_HOST_PROFILE (tuning aid, read once at create): where agar_step_host's wall time goes, printed by agar_destroy
+    bool host_profile = false;
+    double prof_us[4] = {0, 0, 0, 0};  // enqueue | waiting for a chunk's lists | host threads | final stream syncs
+    std::atomic<long long> prof_tsc[5] = {};  // summed over the workers: waiting for a chunk | plan | prefetch | in-place update | full rewrite
+    int64_t prof_calls = 0;
     cudaEvent_t chunk_done[kHostChunks] = {};
     HostPool* pool = nullptr;
     int64_t last_h2d = 0, last_d2h = 0;  // bytes the last agar_step_host call moved over PCIe
@@ -259,6 +273,115 @@ void expand_agent(const DevParams& p, float* dst, const ObsEntry* ent, int count
     _mm_sfence();
 }
 
+// ---- persistent host buffer: bring one agent's grid from the previous step's image to this step's in place ----
+int sentinel_mask(const DevParams& p) {  // channels that carry the -1 out-of-bounds marks (same rule as expand_agent)
+    const int flags = p.c.obs_flags;
+    int m = 0, ch = 0;
+    if (flags & AGAR_OBS_PELLETS) { m |= 1 << ch; ++ch; }
+    if (flags & AGAR_OBS_CELLS) { m |= 1 << ch; ++ch; }
+    if (flags & AGAR_OBS_OTHERS) { if (p.K > 1) m |= 1 << ch; ++ch; }
+    if (flags & AGAR_OBS_VIRUSES) { m |= 1 << ch; ++ch; }
+    if (flags & AGAR_OBS_FOODS) { m |= 1 << ch; ++ch; }
+    return m;
+}
+// What changes between the image described by the previous step's (list, centroid) and this step's.  The world
+// coordinate of grid index i, oob_off[i] + c, does not decrease with i, so the out-of-bounds indices are a prefix
+// (coordinate < 0) and a suffix (coordinate >= arena): index i is in bounds iff lo <= i < hi.
+struct DeltaPlan {
+    int xlo, xhi, ylo, yhi;  // this step's in-bounds rows (x) and columns (y)
+    int rr[2][2];            // two ranges of rows whose state flipped: rewritten whole
+    uint8_t chg[128];        // columns whose state flipped: patched in every unchanged in-bounds row
+    int nchg, smask;
+    bool rows, any, full;    // some row flipped | some index out of bounds now | alive flag flipped: full rewrite
+};
+inline void inbounds_range(const DevParams& p, float c, int& lo, int& hi) {
+    const int G = p.c.grid_size;
+    const float arena = p.c.arena_size;
+    int i = 0;
+    while (i < G && !(0.0f <= p.oob_off[i] + c)) ++i;   // (the same float expression as the raster's rule)
+    lo = i;
+    int j = G;
+    while (j > lo && !(p.oob_off[j - 1] + c < arena)) --j;
+    hi = j;
+}
+void delta_plan(const DevParams& p, const float* pmeta, const float* nmeta, int sentmask, DeltaPlan& d) {
+    const int G = p.c.grid_size;
+    const int sm0 = pmeta[2] != 0.0f ? sentmask : 0, sm1 = nmeta[2] != 0.0f ? sentmask : 0;  // an agent without cells observes zeros
+    d.full = sm0 != sm1; d.smask = sm1; d.nchg = 0; d.rows = false; d.any = false;
+    if (d.full || !sm1) return;
+    int xlo0, xhi0, ylo0, yhi0;
+    inbounds_range(p, pmeta[0], xlo0, xhi0); inbounds_range(p, pmeta[1], ylo0, yhi0);
+    inbounds_range(p, nmeta[0], d.xlo, d.xhi); inbounds_range(p, nmeta[1], d.ylo, d.yhi);
+    d.any = d.xlo > 0 || d.xhi < G || d.ylo > 0 || d.yhi < G;
+    // index i flipped iff it lies between the old and the new bound (lower bounds, upper bounds); when a range is empty
+    // on one side (lo == hi: everything out of bounds) the two intervals may overlap, which only repeats work
+    d.rr[0][0] = xlo0 < d.xlo ? xlo0 : d.xlo; d.rr[0][1] = xlo0 < d.xlo ? d.xlo : xlo0;
+    d.rr[1][0] = xhi0 < d.xhi ? xhi0 : d.xhi; d.rr[1][1] = xhi0 < d.xhi ? d.xhi : xhi0;
+    d.rows = d.rr[0][0] < d.rr[0][1] || d.rr[1][0] < d.rr[1][1];
+    for (int i = (ylo0 < d.ylo ? ylo0 : d.ylo); i < (ylo0 < d.ylo ? d.ylo : ylo0); ++i) d.chg[d.nchg++] = (uint8_t)i;
+    for (int i = (yhi0 < d.yhi ? yhi0 : d.yhi); i < (yhi0 < d.yhi ? d.yhi : yhi0); ++i)
+        if (d.nchg < 128 && !(d.nchg && i <= d.chg[d.nchg - 1])) d.chg[d.nchg++] = (uint8_t)i;
+}
+// Prefetch (for writing) the lines delta_apply will touch: issued for a worker's next agent while it updates the
+// current one, so that the read-for-ownership misses of the scattered stores overlap.
+void delta_prefetch(const DevParams& p, const float* dst, const DeltaPlan& d, const ObsEntry* pe, int pc, const ObsEntry* ne, int nc) {
+    if (d.full) return;
+    for (int e = 0; e < pc; ++e) __builtin_prefetch(dst + pe[e].idx, 1, 3);
+    for (int e = 0; e < nc; ++e) __builtin_prefetch(dst + ne[e].idx, 1, 3);
+    if (!d.smask || !(d.rows || d.nchg)) return;
+    const int G = p.c.grid_size, GG = G * G, C = p.C;
+    const int c0 = d.nchg ? d.chg[0] : 0, c1 = d.nchg ? d.chg[d.nchg - 1] : 0;
+    for (int ch = 0; ch < C; ++ch) {
+        if (!((d.smask >> ch) & 1)) continue;
+        const float* img = dst + (size_t)ch * GG;
+        for (int r = 0; r < 2; ++r)
+            for (int gx = d.rr[r][0]; gx < d.rr[r][1]; ++gx)
+                for (int i = 0; i < G; i += 16) __builtin_prefetch(img + (size_t)gx * G + i, 1, 3);
+        if (d.nchg)
+            for (int gx = d.xlo; gx < d.xhi; ++gx) {
+                __builtin_prefetch(img + (size_t)gx * G + c0, 1, 3);
+                if ((c1 >> 4) != (c0 >> 4)) __builtin_prefetch(img + (size_t)gx * G + c1, 1, 3);
+            }
+    }
+}
+// dst holds the image described by the previous lists; afterwards it holds this step's: the rows whose out-of-bounds
+// state flipped are rewritten, the columns whose state flipped are patched row by row, the bins occupied before are
+// returned to the new base value and the bins occupied now are written.  Plain (cached) stores: only the lines that
+// change are touched.
+void delta_apply(const DevParams& p, float* dst, const DeltaPlan& d, const ObsEntry* pe, int pc, const ObsEntry* ne, int nc,
+                 const float* nmeta) {
+    if (d.full) { expand_agent(p, dst, ne, nc, nmeta); return; }  // the agent died or respawned: rare
+    const int G = p.c.grid_size, GG = G * G, C = p.C, smask = d.smask;
+    if (smask && (d.rows || d.nchg)) {
+        float neg_row[128], col_row[128];
+        for (int i = 0; i < G; ++i) { neg_row[i] = -1.0f; col_row[i] = (i < d.ylo || i >= d.yhi) ? -1.0f : 0.0f; }
+        for (int ch = 0; ch < C; ++ch) {
+            if (!((smask >> ch) & 1)) continue;
+            float* img = dst + (size_t)ch * GG;
+            if (d.nchg)  // (rows that flipped are rewritten whole below; patching them first is harmless)
+                for (int gx = d.xlo; gx < d.xhi; ++gx) {
+                    float* row = img + (size_t)gx * G;
+                    for (int q = 0; q < d.nchg; ++q) row[d.chg[q]] = col_row[d.chg[q]];
+                }
+            for (int r = 0; r < 2; ++r)
+                for (int gx = d.rr[r][0]; gx < d.rr[r][1]; ++gx)
+                    std::memcpy(img + (size_t)gx * G, (gx < d.xlo || gx >= d.xhi) ? neg_row : col_row, (size_t)G * sizeof(float));
+        }
+    }
+    if (!(smask && d.any)) {  // no out-of-bounds mark anywhere in this step's image: the base is zero
+        for (int e = 0; e < pc; ++e) dst[pe[e].idx] = 0.0f;
+    } else {  // idx -> (channel, gx, gy) by multiply-shift (exact for idx < 2^18, divisors <= 2^14)
+        const uint64_t mgg = ((uint64_t)1 << 32) / (uint64_t)GG + 1, mg = ((uint64_t)1 << 32) / (uint64_t)G + 1;
+        for (int e = 0; e < pc; ++e) {
+            const uint32_t idx = pe[e].idx, ch = (uint32_t)(((uint64_t)idx * mgg) >> 32), rel = idx - ch * (uint32_t)GG;
+            const int gx = (int)(((uint64_t)rel * mg) >> 32), gy = (int)rel - gx * G;
+            const bool out = gx < d.xlo || gx >= d.xhi || gy < d.ylo || gy >= d.yhi;
+            dst[idx] = (((smask >> ch) & 1) && out) ? -1.0f : 0.0f;
+        }
+    }
+    for (int e = 0; e < nc; ++e) dst[ne[e].idx] = ne[e].val;
+}
+
 int host_threads_default() {
     if (const char* v = std::getenv("AGAR_HOST_THREADS")) { const int n = std::atoi(v); if (n >= 1 && n <= 256) return n; }
     cpu_set_t set;
@@ -266,6 +389,7 @@ int host_threads_default() {
     int ranks = 1;
     if (const char* v = std::getenv("LOCAL_WORLD_SIZE")) ranks = std::atoi(v) > 0 ? std::atoi(v) : 1;  // one process per GPU share the cores
     int n = avail / ranks;
+    if (n >= 4) n -= 1;  // the calling thread polls the chunk events meanwhile: leave it a core (measured: 15 workers beat 16 on 16 cores)
     return n < 1 ? 1 : (n > 32 ? 32 : n);
 }
 
@@ -307,6 +431,7 @@ int agar_destroy(AgarEnv* e);
 static int create_impl(const AgarConfig* cfg, int device, AgarEnv* e, const cudaDeviceProp& prop) {
     e->device = device;
     e->persist_hash = std::getenv("AGAR_NO_PERSIST") == nullptr;
+    e->host_profile = std::getenv("AGAR_HOST_PROFILE") != nullptr;
     DevParams& p = e->p;
     std::memset(&p, 0, sizeof(p));
     p.c = *cfg;
@@ -414,6 +539,14 @@ int agar_create(const AgarConfig* cfg, int device, AgarEnv** out) {
 int agar_destroy(AgarEnv* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
+    if (e->host_profile && e->prof_calls > 0)
+        std::fprintf(stderr, "[agar_step_host] %lld calls, us per call: enqueue %.0f | wait for lists %.0f | host threads %.0f | final syncs %.0f\n",
+                     (long long)e->prof_calls, e->prof_us[0] / e->prof_calls, e->prof_us[1] / e->prof_calls, e->prof_us[2] / e->prof_calls,
+                     e->prof_us[3] / e->prof_calls);
+    if (e->host_profile && e->prof_calls > 0 && e->pool)
+        std::fprintf(stderr, "[agar_step_host] worker kilo-cycles per call, summed over the workers: waiting %lld | plan %lld | prefetch %lld | in-place %lld | full rewrite %lld\n",
+                     e->prof_tsc[0].load() / e->prof_calls / 1000, e->prof_tsc[1].load() / e->prof_calls / 1000, e->prof_tsc[2].load() / e->prof_calls / 1000,
+                     e->prof_tsc[3].load() / e->prof_calls / 1000, e->prof_tsc[4].load() / e->prof_calls / 1000);
     cudaFree(e->d_order); cudaFree(e->d_state); cudaFree(e->d_events); cudaFree(e->d_ev_counts); cudaFree(e->d_hash);
     cudaFree(e->d_tab_xy); cudaFree(e->d_tab_act);
     cudaFree(e->d_target); cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_reward); cudaFree(e->d_done);
@@ -595,9 +728,9 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
         cudaError_t err = cudaMalloc(&e->d_entries, NA * cap * sizeof(ObsEntry));
         if (err == cudaSuccess) err = cudaMalloc(&e->d_counts, NA * sizeof(int32_t));
         if (err == cudaSuccess) err = cudaMalloc(&e->d_meta, NA * 4 * sizeof(float));
-        if (err == cudaSuccess) err = cudaMallocHost(&e->h_entries, NA * cap * sizeof(ObsEntry));
-        if (err == cudaSuccess) err = cudaMallocHost(&e->h_counts, NA * sizeof(int32_t));
-        if (err == cudaSuccess) err = cudaMallocHost(&e->h_meta, NA * 4 * sizeof(float));
+        if (err == cudaSuccess) err = cudaMallocHost(&e->h_entries, 2 * NA * cap * sizeof(ObsEntry));
+        if (err == cudaSuccess) err = cudaMallocHost(&e->h_counts, 2 * NA * sizeof(int32_t));
+        if (err == cudaSuccess) err = cudaMallocHost(&e->h_meta, 2 * NA * 4 * sizeof(float));
         for (int k = 0; k < kHostChunks && err == cudaSuccess; ++k) err = cudaEventCreateWithFlags(&e->chunk_done[k], cudaEventDisableTiming);
         if (err != cudaSuccess) return fail(std::string("agar_step_host: compact-copy allocation failed: ") + cudaGetErrorString(err));
         e->pool = new (std::nothrow) HostPool(host_threads_default());
@@ -606,6 +739,18 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
         e->host_compact = true;
     }
     const bool compact = h_obs && e->host_compact;
+    // this call fills the half of the pinned list buffers the previous one did not; with a persistent h_obs the previous
+    // half says what the buffer holds and the grids are updated in place
+    const int cur = e->hbuf ^ 1;
+    const bool delta = compact && e->host_persistent && e->delivered == h_obs;
+    e->delivered = nullptr;  // (set again once this call has completed)
+    const size_t half = compact ? (size_t)cur * NA : 0, other = compact ? (size_t)(cur ^ 1) * NA : 0;
+    ObsEntry* const h_ent = e->h_entries + half * (size_t)e->entry_cap;
+    int32_t* const h_cnt = e->h_counts + half;
+    float* const h_met = e->h_meta + half * 4;
+    const ObsEntry* const p_ent = e->h_entries + other * (size_t)e->entry_cap;
+    const int32_t* const p_cnt = e->h_counts + other;
+    const float* const p_met = e->h_meta + other * 4;
     // The private streams are non-blocking: order them after whatever the caller enqueued on its own stream(s)
     // (agar_reset, agar_step, agar_set_state ...) since the previous host-buffer step.
     if (e->pending) {
@@ -617,6 +762,10 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
         e->pending = false; e->pending_multi = false;
     }
     cudaStream_t st = e->host_stream, st2 = e->host_stream2;
+    const bool prof = e->host_profile;
+    auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mark = prof ? now_us() : 0.0;
+    auto lap = [&](int slot) { if (prof) { const double t = now_us(); e->prof_us[slot] += t - t_mark; t_mark = t; } };
     e->last_h2d = (int64_t)(NA * 2 * sizeof(float) + NA * sizeof(int32_t));
     e->last_d2h = (int64_t)(NA * sizeof(float) + NA);
     CUDA_OK(cudaMemcpyAsync(e->d_target, h_target_xy, NA * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -625,6 +774,58 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
     // it, overlap the kernel of the next (compute stream).
     const int chunks = (h_obs && N >= 1024) ? kHostChunks : 1;
     const int cap = e->entry_cap;
+    // One job per call: the workers are woken now (their wake-up overlaps the first chunk's kernel) and go through the
+    // chunks in order, each as soon as `ready` says its lists have landed; kAbort releases them when the call fails.
+    constexpr int kAbort = 1 << 30;
+    std::atomic<int> ready{0};
+    std::function<void(int, int)> job;
+    struct JobGuard {
+        HostPool* pool; std::atomic<int>* ready; bool active;
+        ~JobGuard() { if (active) { ready->store(kAbort, std::memory_order_release); pool->wait(); } }
+    } guard{e->pool, &ready, false};
+    if (compact) {
+        const AgarEnv* ce = e;
+        const int sentmask = sentinel_mask(e->p);
+        std::atomic<int>* rdy = &ready;
+        std::atomic<long long>* ptsc = prof ? e->prof_tsc : nullptr;
+        job = [=](int w, int nw) {
+            DeltaPlan plan[2];
+            long long tsc[5] = {0, 0, 0, 0, 0}, t_last = ptsc ? (long long)__rdtsc() : 0;
+            auto tick = [&](int slot) { if (ptsc) { const long long t = (long long)__rdtsc(); tsc[slot] += t - t_last; t_last = t; } };
+            auto in_place = [&](size_t g) { return delta && h_cnt[g] <= cap && p_cnt[g] <= cap; };  // (an image copied whole has no list)
+            for (int k = 0; k < chunks; ++k) {
+                const size_t g0 = (size_t)(N * k / chunks) * A, g1 = (size_t)(N * (k + 1) / chunks) * A;
+                for (int spins = 0;; ++spins) {
+                    const int r = rdy->load(std::memory_order_acquire);
+                    if (r >= kAbort) return;
+                    if (r > k) break;
+                    if ((spins & 1023) == 1023) std::this_thread::yield(); else _mm_pause();
+                }
+                tick(0);
+                int pi = 0;
+                const size_t gf = g0 + (size_t)w;
+                if (gf < g1 && in_place(gf)) delta_plan(ce->p, p_met + gf * 4, h_met + gf * 4, sentmask, plan[0]);
+                for (size_t g = gf; g < g1; g += (size_t)nw) {
+                    const size_t gn = g + (size_t)nw;  // this worker's next agent: plan it and start its misses now
+                    if (gn < g1 && in_place(gn)) {
+                        delta_plan(ce->p, p_met + gn * 4, h_met + gn * 4, sentmask, plan[pi ^ 1]);
+                        tick(1);
+                        delta_prefetch(ce->p, h_obs + gn * per_agent, plan[pi ^ 1], p_ent + gn * cap, p_cnt[gn], h_ent + gn * cap, h_cnt[gn]);
+                        tick(2);
+                    }
+                    const int cnt = h_cnt[g];
+                    if (cnt <= cap) {  // (an overflowed list: the calling thread has the image copied whole)
+                        if (in_place(g)) { delta_apply(ce->p, h_obs + g * per_agent, plan[pi], p_ent + g * cap, p_cnt[g], h_ent + g * cap, cnt, h_met + g * 4); tick(3); }
+                        else { expand_agent(ce->p, h_obs + g * per_agent, h_ent + g * cap, cnt, h_met + g * 4); tick(4); }
+                    }
+                    pi ^= 1;
+                }
+            }
+            if (ptsc) for (int i = 0; i < 5; ++i) ptsc[i].fetch_add(tsc[i], std::memory_order_relaxed);
+        };
+        e->pool->start(job);
+        guard.active = true;
+    }
     for (int k = 0; k < chunks; ++k) {
         const int a0 = (int)(N * k / chunks), a1 = (int)(N * (k + 1) / chunks);
         KArgs a = base_args(e);
@@ -645,9 +846,9 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
         CUDA_OK(cudaEventRecord(e->host_event, st));
         CUDA_OK(cudaStreamWaitEvent(st2, e->host_event, 0));
         if (compact) {
-            CUDA_OK(cudaMemcpyAsync(e->h_entries + g0 * cap, e->d_entries + g0 * cap, gn * cap * sizeof(ObsEntry), cudaMemcpyDeviceToHost, st2));
-            CUDA_OK(cudaMemcpyAsync(e->h_counts + g0, e->d_counts + g0, gn * sizeof(int32_t), cudaMemcpyDeviceToHost, st2));
-            CUDA_OK(cudaMemcpyAsync(e->h_meta + g0 * 4, e->d_meta + g0 * 4, gn * 4 * sizeof(float), cudaMemcpyDeviceToHost, st2));
+            CUDA_OK(cudaMemcpyAsync(h_ent + g0 * cap, e->d_entries + g0 * cap, gn * cap * sizeof(ObsEntry), cudaMemcpyDeviceToHost, st2));
+            CUDA_OK(cudaMemcpyAsync(h_cnt + g0, e->d_counts + g0, gn * sizeof(int32_t), cudaMemcpyDeviceToHost, st2));
+            CUDA_OK(cudaMemcpyAsync(h_met + g0 * 4, e->d_meta + g0 * 4, gn * 4 * sizeof(float), cudaMemcpyDeviceToHost, st2));
             CUDA_OK(cudaEventRecord(e->chunk_done[k], st2));
             e->last_d2h += (int64_t)(gn * cap * sizeof(ObsEntry) + gn * sizeof(int32_t) + gn * 4 * sizeof(float));
         } else {
@@ -658,28 +859,35 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
     }
     CUDA_OK(cudaMemcpyAsync(h_reward, e->d_reward, NA * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaMemcpyAsync(h_done, e->d_done, NA, cudaMemcpyDeviceToHost, st));
+    lap(0);
     if (compact) {
-        for (int k = 0; k < chunks; ++k) {  // rebuild the dense grids of a chunk as soon as its lists have landed
+        for (int k = 0; k < chunks; ++k) {  // hand each chunk to the workers as soon as its lists have landed
             const size_t g0 = (size_t)(N * k / chunks) * A, g1 = (size_t)(N * (k + 1) / chunks) * A;
             CUDA_OK(cudaEventSynchronize(e->chunk_done[k]));
-            const AgarEnv* ce = e;
-            const std::function<void(int, int)> job = [ce, g0, g1, cap, per_agent, h_obs](int w, int nw) {
-                for (size_t g = g0 + (size_t)w; g < g1; g += (size_t)nw) {
-                    const int cnt = ce->h_counts[g];
-                    if (cnt > cap) continue;  // overflowed list: the image is copied whole below
-                    expand_agent(ce->p, h_obs + g * per_agent, ce->h_entries + g * cap, cnt, ce->h_meta + g * 4);
-                }
-            };
-            e->pool->run(job);
-            for (size_t g = g0; g < g1; ++g)
-                if (e->h_counts[g] > cap) {
+            ready.store(k + 1, std::memory_order_release);
+            for (size_t g = g0; g < g1; ++g)  // an overflowed list: the image is copied whole (the workers skip the agent)
+                if (h_cnt[g] > cap) {
                     CUDA_OK(cudaMemcpyAsync(h_obs + g * per_agent, e->d_obs + g * per_agent, per_agent * sizeof(float), cudaMemcpyDeviceToHost, st2));
                     e->last_d2h += (int64_t)(per_agent * sizeof(float));
                 }
         }
+        lap(1);
+        e->pool->wait();
+        guard.active = false;
+        lap(2);
     }
     CUDA_OK(cudaStreamSynchronize(st));
     CUDA_OK(cudaStreamSynchronize(st2));
+    lap(3);
+    if (prof) e->prof_calls += 1;
+    if (compact) { e->hbuf = cur; e->delivered = h_obs; }
+    return 0;
+}
+
+int agar_host_obs_persistent(AgarEnv* e, int on) {
+    if (!e) return fail("env is NULL");
+    e->host_persistent = on != 0;
+    e->delivered = nullptr;  // the next call rewrites every grid in full
     return 0;
 }
 

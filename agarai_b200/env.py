@@ -327,6 +327,12 @@ class BatchedAgarioEnv:
             return
         _lib.check(self._L.agar_step_host(self._h, vp(target_xy), vp(act), vp(obs), vp(reward), vp(done)), self._L)
 
+    def host_obs_persistent(self, on: bool = True):
+        """agar_host_obs_persistent: promise that consecutive step_host calls receive the same, untouched `obs` array;
+        the library then rewrites only what changed between two steps (bit-identical grids, several times less host
+        memory traffic).  Use it when the env owns its observation buffer, as vector envs do."""
+        _lib.check(self._L.agar_host_obs_persistent(self._h, 1 if on else 0), self._L)
+
     def host_copy_bytes(self):
         """(host->device, device->host) bytes of the last step_host call"""
         h2d, d2h = C.c_int64(0), C.c_int64(0)

@@ -461,14 +461,21 @@ def run_cuda(args):
     h_obs = torch.empty(env.obs_shape, dtype=torch.float32).pin_memory()
     h_rew = torch.empty((N, A), dtype=torch.float32).pin_memory()
     h_done = torch.empty((N, A), dtype=torch.uint8).pin_memory()
-    env.step_host(h_xy[0].numpy(), h_act[0].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())  # warm-up
-    ctx.barrier()
-    t0 = time.perf_counter()
-    for i in range(Ke):
-        env.step_host(h_xy[i].numpy(), h_act[i].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())
-    torch.cuda.synchronize(ctx.dev)
-    e2e_local = time.perf_counter() - t0
-    e2e_value = ctx.world * N * Ke / sharding.max_over_ranks(e2e_local, ctx.dev)
+    def e2e_run():
+        env.step_host(h_xy[0].numpy(), h_act[0].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())  # warm-up
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            env.step_host(h_xy[i].numpy(), h_act[i].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())
+        torch.cuda.synchronize(ctx.dev)
+        dt = time.perf_counter() - t0
+        return dt, ctx.world * N * Ke / sharding.max_over_ranks(dt, ctx.dev)
+
+    # (1) every grid streamed out in full each step (any h_obs, the library's default); (2) the env-owned observation
+    # buffer of a vector env: the same pinned buffer every step, declared with agar_host_obs_persistent, updated in place
+    _, e2e_full = e2e_run()
+    env.host_obs_persistent(True)
+    e2e_local, e2e_value = e2e_run()
     h2d, d2h = env.host_copy_bytes()            # what the last call moved over PCIe (compact copy: occupied bins, not grids)
     delivered = h_obs.numel() * 4 + N * A * (4 + 1)   # what the caller received in its host buffers
     e2e_gbs_local = delivered * Ke / e2e_local / 1e9
@@ -495,9 +502,12 @@ def run_cuda(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "host_bytes_delivered_per_step": delivered, "host_delivery_gbs_rank0": e2e_gbs_local,
-                    "api": "agar_step_host: actions from pinned host memory, dense float32 grids + rewards + dones delivered into pinned "
-                           "host buffers every step (4 chunks; grids cross PCIe as per-agent occupied-bin lists and are rebuilt by the "
-                           "library's host threads while the next chunk runs)"},
+                    "full_rewrite_value": e2e_full,
+                    "api": "agar_step_host: actions from pinned host memory, dense float32 grids + rewards + dones in pinned host "
+                           "buffers after every step (4 chunks; grids cross PCIe as per-agent occupied-bin lists and the library's host "
+                           "threads bring the caller's grids up to date while the next chunk runs).  `value`: the env-owned observation "
+                           "buffer of a vector env (same buffer every step, agar_host_obs_persistent: only the lines that changed are "
+                           "rewritten, grids bit-identical); `full_rewrite_value`: the default, every grid streamed out in full"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": frac,
                          "traffic": ncu_traffic_bytes(args.world, N) if not args.set else None, "kernel": "agar_step_kernel",

@@ -161,6 +161,60 @@ def test_num_frames_stacks_the_last_k_grids(oracle):
     one.close()
 
 
+@pytest.mark.parametrize("world", ["borders_multi_agent", "single_player", "dense_overflow", "cfg2"])
+def test_step_host_persistent_buffer_updates_in_place(world):
+    """agar_host_obs_persistent: with the caller's promise that h_obs is the same untouched memory from call to call, the
+    host side rewrites only what changed since the previous step (bins that were / become occupied, out-of-bounds rows
+    and columns that moved).  The buffer must equal the device observation bit for bit after every step: agents
+    crossing the arena border (sentinel rows and columns shift), agents dying and arenas resetting, images fuller than
+    the list capacity (copied whole, then rebuilt in full), a call with another buffer in between, a masked reset and a
+    switch off / on of the mode."""
+    import agarai_b200 as ab
+    import bench
+    kw = {
+        "borders_multi_agent": dict(num_arenas=160, num_agents=3, num_bots=4, num_viruses=5, num_pellets=300, arena_size=150.0,
+                                    view_size=100.0, grid_size=32, obs_flags=31, start_mass=40.0, virus_pop_mass=60.0, virus_mass=30.0,
+                                    auto_reset=1, speed_k=8.0),
+        "single_player": dict(num_arenas=300, num_agents=1, num_bots=0, num_pellets=200, arena_size=90.0, view_size=128.0,
+                              grid_size=64, obs_flags=7),
+        "dense_overflow": dict(num_arenas=1100, num_agents=1, num_bots=1, num_pellets=900, arena_size=200.0, view_size=128.0,
+                               grid_size=64, obs_flags=7, speed_k=8.0),
+        "cfg2": dict(bench.WORLDS["cfg2"], num_arenas=1024),
+    }[world]
+    a = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=33)
+    b = ab.BatchedAgarioEnv(ab.default_config(**kw), seed=33)
+    a.reset(); b.reset()
+    b.host_obs_persistent(True)
+    N, A = kw["num_arenas"], kw["num_agents"]
+    rng = np.random.default_rng(2)
+    h_obs = torch.empty(b.obs_shape, dtype=torch.float32).pin_memory()
+    other = torch.empty(b.obs_shape, dtype=torch.float32).pin_memory()
+    h_obs.fill_(7.0); other.fill_(-3.0)  # stale content before the first delivery into each buffer
+    h_r = torch.empty((N, A), dtype=torch.float32).pin_memory(); h_d = torch.empty((N, A), dtype=torch.uint8).pin_memory()
+    partial = 0
+    for t in range(60):
+        xy = rng.uniform(-1, 1, (N, A, 2)).astype(f32)
+        xy[: N // 2] = np.sign(xy[: N // 2, :, :1]) * np.array([1.0, 0.3], f32)  # half of the arenas run into the side walls
+        act = rng.integers(0, 3, (N, A)).astype(np.int32)
+        if t == 20:  # a masked reset on both sides: the device state jumps, the host buffer still holds step 19's grids
+            m = torch.from_numpy((rng.random(N) < 0.3).astype(np.uint8)).cuda()
+            a.reset(mask=m); b.reset(mask=m)
+        if t == 30:
+            b.host_obs_persistent(False)
+        if t == 33:
+            b.host_obs_persistent(True)
+        o, r, d, _ = a.step(torch.from_numpy(xy).cuda(), torch.from_numpy(act).cuda())
+        buf = other if t in (10, 11, 40) else h_obs  # another pointer: full rewrite there, and again on the way back
+        b.step_host(xy, act, buf.numpy(), h_r.numpy(), h_d.numpy())
+        assert np.array_equal(buf.numpy().view(np.int32), o.cpu().numpy().view(np.int32)), f"{world}: obs differ at step {t}"
+        assert np.array_equal(h_r.numpy(), r.cpu().numpy()) and np.array_equal(h_d.numpy(), d.cpu().numpy())
+        occ = ((o != 0) & (o != -1)).flatten(2).sum(2)
+        partial += int(((occ > 256).any() and (occ <= 256).any()).item())
+    if world == "dense_overflow":
+        assert partial > 10, "expected steps with both listed and overflowed images"
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("world", ["borders_multi_agent", "single_player", "dense_overflow"])
 def test_step_host_compact_copy_rebuilds_identical_grids(world):
     """agar_step_host with batches of >= 256 agents copies per-agent lists of occupied bins + centroids and rebuilds the
