@@ -63,6 +63,9 @@ class Coordinator:
         self._obs = torch.zeros(self.env.obs_shape, dtype=torch.float32).pin_memory()
         self._r = torch.zeros((N, A), dtype=torch.float32).pin_memory()
         self._d = torch.zeros((N, A), dtype=torch.uint8).pin_memory()
+        # _obs is private to this object and only step_host writes to it (callers get copies, _env_obs): the library
+        # may update it in place from step to step instead of rewriting every grid
+        self.env.host_obs_persistent(True)
 
     def __enter__(self):
         self.open()

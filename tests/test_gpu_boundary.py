@@ -215,6 +215,35 @@ def test_step_host_persistent_buffer_updates_in_place(world):
     a.close(); b.close()
 
 
+def test_coordinator_with_hundreds_of_workers_updates_its_buffer_in_place():
+    """a2c/coordinator.py semantics at a batch size where agar_step_host takes the compact copy: the Coordinator owns its
+    pinned observation buffer, hands out copies and declares the buffer persistent; every live env's observation must
+    equal the device-resident twin's, step after step."""
+    import agarai_b200 as ab
+    kw = dict(num_agents=1, multi_agent=False, difficulty="normal", num_pellets=300, num_viruses=3, num_bots=6, arena_size=120.0,
+              grid_size=32, observe_viruses=True, start_mass=12.0)
+    W = 320
+    twin = ab.BatchedAgarioEnv(ab.config_from_gym_kwargs(num_envs=W, auto_reset=0, **kw), seed=4)
+    rng = np.random.default_rng(3)
+    with ab.Coordinator(lambda: kw, W, seed=4) as coord:
+        obs = coord.reset()
+        o_dev = twin.reset().cpu().numpy()
+        assert all(np.array_equal(obs[i], o_dev[i, 0]) for i in range(W))
+        for t in range(40):
+            xy = rng.uniform(-1, 1, (W, 2)).astype(f32); act = rng.integers(0, 3, W).astype(np.int32)
+            live = [not d for d in coord.dones]
+            xy_d = np.where(np.array(live)[:, None], xy, 0).astype(f32); act_d = np.where(live, act, 0).astype(np.int32)
+            obs, rs, dones, _ = coord.step([(float(xy[i, 0]), float(xy[i, 1]), int(act[i])) for i in range(W)])
+            o, r, d, _ = twin.step(torch.from_numpy(xy_d.reshape(W, 1, 2)).cuda(), torch.from_numpy(act_d.reshape(W, 1)).cuda())
+            o = o.cpu().numpy(); r = r.cpu().numpy()
+            for i in range(W):
+                if live[i]:
+                    assert np.array_equal(obs[i].view(np.int32), o[i, 0].view(np.int32)) and rs[i] == r[i, 0], (t, i)
+                else:
+                    assert obs[i] is None
+    twin.close()
+
+
 @pytest.mark.parametrize("world", ["borders_multi_agent", "single_player", "dense_overflow"])
 def test_step_host_compact_copy_rebuilds_identical_grids(world):
     """agar_step_host with batches of >= 256 agents copies per-agent lists of occupied bins + centroids and rebuilds the
