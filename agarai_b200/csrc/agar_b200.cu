@@ -3,8 +3,10 @@
 #include <cuda_runtime.h>
 
 #include <immintrin.h>
+#include <pthread.h>
 #include <sched.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
@@ -73,47 +75,111 @@ class HostPool {
 public:
     explicit HostPool(int n) : n_(n) {
         for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { loop(i); });
+        pin();
+    }
+    // Each worker stays on one core of this rank's share of the process's CPU set (AGAR_HOST_PIN=0 leaves them to the
+    // scheduler): worker w updates the same agents every step, and the lines it wrote in the previous step - the bins it
+    // now clears - are still in that core's L2; ranks sharing a host keep out of each other's cores.
+    void pin() {
+        if (const char* v = std::getenv("AGAR_HOST_PIN")) if (std::atoi(v) == 0) return;
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) != 0) return;
+        std::vector<int> cpus;
+        for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &set)) cpus.push_back(c);
+        int ranks = 1, rank = 0;
+        if (const char* v = std::getenv("LOCAL_WORLD_SIZE")) ranks = std::atoi(v) > 0 ? std::atoi(v) : 1;
+        if (const char* v = std::getenv("LOCAL_RANK")) rank = std::atoi(v);
+        const int per = (int)cpus.size() / ranks;
+        if (per < 2 || rank < 0 || rank >= ranks || n_ >= per) return;
+        caller_cpu_ = cpus[(size_t)rank * per];
+        for (int i = 0; i < n_; ++i) {  // the share's first core is left to the calling thread (CallerPin)
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(cpus[(size_t)rank * per + (size_t)((i + 1) % per)], &one);
+            pthread_setaffinity_np(th_[(size_t)i].native_handle(), sizeof(one), &one);
+        }
     }
     ~HostPool() {
-        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; gen_.fetch_add(1, std::memory_order_release); }
         cv_.notify_all();
         for (auto& t : th_) t.join();
     }
-    // start(fn) hands fn to every worker and returns; wait() returns when all of them are done (fn must live until then)
+    // start(fn) hands fn to every worker and returns; wait() returns when all of them are done (fn must live until then).
+    // Neither side sleeps while a call is in flight: a sleeping vCPU of this kind of host takes 50-150 us to come back
+    // (measured as a bimodal tail of the call).  A worker polls for the next job for a grace period after finishing one
+    // (back-to-back calls find it awake), then sleeps on the condition variable; wait() polls the pending counter.
     void start(const std::function<void(int, int)>& fn) {
-        std::lock_guard<std::mutex> lk(m_);
-        job_ = &fn; ++gen_; pending_ = n_;
-        cv_.notify_all();
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            job_ = &fn;
+            pending_.store(n_, std::memory_order_relaxed);
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
     }
     void wait() {
-        std::unique_lock<std::mutex> lk(m_);
-        done_.wait(lk, [&] { return pending_ == 0; });
+        for (int spins = 0; pending_.load(std::memory_order_acquire) != 0; ++spins)
+            if ((spins & 4095) == 4095) std::this_thread::yield(); else _mm_pause();
     }
+    int caller_cpu() const { return caller_cpu_; }
+    int size() const { return n_; }
 
 private:
     void loop(int i) {
         int seen = 0;
         for (;;) {
-            std::unique_lock<std::mutex> lk(m_);
-            cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
-            if (stop_) return;
-            seen = gen_;
-            const std::function<void(int, int)>* f = job_;
-            lk.unlock();
+            // poll for ~200 us, then sleep
+            const auto t0 = std::chrono::steady_clock::now();
+            bool got = false;
+            for (int spins = 0;; ++spins) {
+                if (gen_.load(std::memory_order_acquire) != seen) { got = true; break; }
+                _mm_pause();
+                if ((spins & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+            }
+            if (!got) {
+                std::unique_lock<std::mutex> lk(m_);
+                sleepers_.fetch_add(1, std::memory_order_acq_rel);
+                cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+                sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+            }
+            const std::function<void(int, int)>* f;
+            {
+                std::lock_guard<std::mutex> lk(m_);  // (job_ and stop_ are written under the lock, before gen_ moves)
+                if (stop_) return;
+                seen = gen_.load(std::memory_order_acquire);
+                f = job_;
+            }
             (*f)(i, n_);
-            lk.lock();
-            if (--pending_ == 0) done_.notify_one();
+            pending_.fetch_sub(1, std::memory_order_acq_rel);
         }
     }
+    int caller_cpu_ = -1;  // >= 0 when the workers are pinned: the core of this rank's share they leave free
     int n_;
     std::vector<std::thread> th_;
     std::mutex m_;
-    std::condition_variable cv_, done_;
+    std::condition_variable cv_;
     const std::function<void(int, int)>* job_ = nullptr;
-    int gen_ = 0, pending_ = 0;
+    std::atomic<int> gen_{0}, pending_{0}, sleepers_{0};
     bool stop_ = false;
 };
 
+// While agar_step_host polls the chunk events its thread stays on the core the pinned workers leave free, so that it
+// never shares a core with one of them; the caller's affinity mask is restored on return.
+struct CallerPin {
+    cpu_set_t saved;
+    bool active = false;
+    explicit CallerPin(int cpu) {
+        if (cpu < 0 || sched_getaffinity(0, sizeof(saved), &saved) != 0) return;
+        cpu_set_t one;
+        CPU_ZERO(&one);
+        CPU_SET(cpu, &one);
+        active = sched_setaffinity(0, sizeof(one), &one) == 0;
+    }
+    ~CallerPin() { if (active) sched_setaffinity(0, sizeof(saved), &saved); }
+};
+
+constexpr int kMaxWorkers = 32;  // (host_threads_default caps the pool at 32)
+struct alignas(64) TakeCounter { std::atomic<int> v{0}; };  // one cache line each: owners and thieves of different lists do not collide
 constexpr int kHostChunks = 4;   // agar_step_host steps the batch in chunks: copies and host work overlap the next kernel
 constexpr int kEntryCap = 256;   // (index, value) pairs kept per agent image; a fuller image is copied whole
 
@@ -153,17 +219,20 @@ struct AgarEnv {
     // compact device-to-host copy of agar_step_host (obs_compact_kernel): occupied bins + centroids instead of images
     bool host_compact = false;
     int entry_cap = 0;
-    ObsEntry* d_entries = nullptr; int32_t* d_counts = nullptr; float* d_meta = nullptr;
-    ObsEntry* h_entries = nullptr; int32_t* h_counts = nullptr; float* h_meta = nullptr;  // pinned, two halves: this step's / the previous step's
+    ObsEntry* d_entries = nullptr; float* d_meta = nullptr;  // meta: per agent {centroid x, y, has cells, list length (int32 bits)}
+    ObsEntry* h_entries = nullptr; float* h_meta = nullptr;  // pinned, two halves: this step's / the previous step's
     // persistent host observation buffer (agar_host_obs_persistent): the previous step's lists describe what h_obs holds
     bool host_persistent = false;
-    int hbuf = 0;                      // which half of h_entries / h_counts / h_meta the last completed call filled
+    int hbuf = 0;                      // which half of h_entries / h_meta the last completed call filled
     const float* delivered = nullptr;  // h_obs of the last completed compact call (nullptr: contents unknown)
     // AGAR_HOST_PROFILE (tuning aid, read once at create): where agar_step_host's wall time goes, printed by agar_destroy
     bool host_profile = false;
     double prof_us[4] = {0, 0, 0, 0};  // enqueue | waiting for a chunk's lists | host threads | final stream syncs
     std::atomic<long long> prof_tsc[5] = {};  // summed over the workers: waiting for a chunk | plan | prefetch | in-place update | full rewrite
     int64_t prof_calls = 0;
+    TakeCounter* take = nullptr;        // [kHostChunks][kMaxWorkers] agents taken from each worker's list of each chunk (this call)
+    long long prof_fin[64] = {};       // TSC at which each worker finished the call's job
+    double prof_spread[3] = {0, 0, 0};  // kilo-cycles from the last chunk's publication to the first / median / last worker's finish
     cudaEvent_t chunk_done[kHostChunks] = {};
     HostPool* pool = nullptr;
     int64_t last_h2d = 0, last_d2h = 0;  // bytes the last agar_step_host call moved over PCIe
@@ -383,7 +452,7 @@ void delta_apply(const DevParams& p, float* dst, const DeltaPlan& d, const ObsEn
 }
 
 int host_threads_default() {
-    if (const char* v = std::getenv("AGAR_HOST_THREADS")) { const int n = std::atoi(v); if (n >= 1 && n <= 256) return n; }
+    if (const char* v = std::getenv("AGAR_HOST_THREADS")) { const int n = std::atoi(v); if (n >= 1 && n <= kMaxWorkers) return n; }
     cpu_set_t set;
     int avail = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
     int ranks = 1;
@@ -544,6 +613,9 @@ int agar_destroy(AgarEnv* e) {
                      (long long)e->prof_calls, e->prof_us[0] / e->prof_calls, e->prof_us[1] / e->prof_calls, e->prof_us[2] / e->prof_calls,
                      e->prof_us[3] / e->prof_calls);
     if (e->host_profile && e->prof_calls > 0 && e->pool)
+        std::fprintf(stderr, "[agar_step_host] kilo-cycles from the last chunk's publication to the first / median / last worker's finish: %.0f / %.0f / %.0f\n",
+                     e->prof_spread[0] / e->prof_calls, e->prof_spread[1] / e->prof_calls, e->prof_spread[2] / e->prof_calls);
+    if (e->host_profile && e->prof_calls > 0 && e->pool)
         std::fprintf(stderr, "[agar_step_host] worker kilo-cycles per call, summed over the workers: waiting %lld | plan %lld | prefetch %lld | in-place %lld | full rewrite %lld\n",
                      e->prof_tsc[0].load() / e->prof_calls / 1000, e->prof_tsc[1].load() / e->prof_calls / 1000, e->prof_tsc[2].load() / e->prof_calls / 1000,
                      e->prof_tsc[3].load() / e->prof_calls / 1000, e->prof_tsc[4].load() / e->prof_calls / 1000);
@@ -555,8 +627,9 @@ int agar_destroy(AgarEnv* e) {
     if (e->host_event) cudaEventDestroy(e->host_event);
     if (e->order_event) cudaEventDestroy(e->order_event);
     delete e->pool;
-    cudaFree(e->d_entries); cudaFree(e->d_counts); cudaFree(e->d_meta);
-    cudaFreeHost(e->h_entries); cudaFreeHost(e->h_counts); cudaFreeHost(e->h_meta);
+    delete[] e->take;
+    cudaFree(e->d_entries); cudaFree(e->d_meta);
+    cudaFreeHost(e->h_entries); cudaFreeHost(e->h_meta);
     for (int k = 0; k < kHostChunks; ++k)
         if (e->chunk_done[k]) cudaEventDestroy(e->chunk_done[k]);
     delete e;
@@ -724,21 +797,23 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
     // images stay on the device, the host receives each agent's centroid and occupied bins and rebuilds the dense
     // grids with its own threads.  201 MB -> 8.5 MB over PCIe per step of 4096 cfg2 arenas.
     if (h_obs && !e->entry_cap && NA >= 256 && !std::getenv("AGAR_HOST_DENSE")) {
-        const int cap = per_agent < (size_t)kEntryCap ? (int)per_agent : kEntryCap;
+        int want = kEntryCap;
+        if (const char* v = std::getenv("AGAR_ENTRY_CAP")) { const int n = std::atoi(v); if (n >= 16 && n <= 4096) want = n; }  // tuning switch
+        const int cap = per_agent < (size_t)want ? (int)per_agent : want;
         cudaError_t err = cudaMalloc(&e->d_entries, NA * cap * sizeof(ObsEntry));
-        if (err == cudaSuccess) err = cudaMalloc(&e->d_counts, NA * sizeof(int32_t));
         if (err == cudaSuccess) err = cudaMalloc(&e->d_meta, NA * 4 * sizeof(float));
         if (err == cudaSuccess) err = cudaMallocHost(&e->h_entries, 2 * NA * cap * sizeof(ObsEntry));
-        if (err == cudaSuccess) err = cudaMallocHost(&e->h_counts, 2 * NA * sizeof(int32_t));
         if (err == cudaSuccess) err = cudaMallocHost(&e->h_meta, 2 * NA * 4 * sizeof(float));
         for (int k = 0; k < kHostChunks && err == cudaSuccess; ++k) err = cudaEventCreateWithFlags(&e->chunk_done[k], cudaEventDisableTiming);
         if (err != cudaSuccess) return fail(std::string("agar_step_host: compact-copy allocation failed: ") + cudaGetErrorString(err));
         e->pool = new (std::nothrow) HostPool(host_threads_default());
-        if (!e->pool) return fail("out of host memory");
+        e->take = new (std::nothrow) TakeCounter[kHostChunks * kMaxWorkers];
+        if (!e->pool || !e->take) return fail("out of host memory");
         e->entry_cap = cap;
         e->host_compact = true;
     }
     const bool compact = h_obs && e->host_compact;
+    CallerPin caller_pin(compact && e->pool ? e->pool->caller_cpu() : -1);
     // this call fills the half of the pinned list buffers the previous one did not; with a persistent h_obs the previous
     // half says what the buffer holds and the grids are updated in place
     const int cur = e->hbuf ^ 1;
@@ -746,11 +821,12 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
     e->delivered = nullptr;  // (set again once this call has completed)
     const size_t half = compact ? (size_t)cur * NA : 0, other = compact ? (size_t)(cur ^ 1) * NA : 0;
     ObsEntry* const h_ent = e->h_entries + half * (size_t)e->entry_cap;
-    int32_t* const h_cnt = e->h_counts + half;
     float* const h_met = e->h_meta + half * 4;
     const ObsEntry* const p_ent = e->h_entries + other * (size_t)e->entry_cap;
-    const int32_t* const p_cnt = e->h_counts + other;
     const float* const p_met = e->h_meta + other * 4;
+    // an agent's record in the meta arrays: {centroid x, centroid y, has cells, length of its list as int32 bits}
+    const auto h_cnt = [h_met](size_t g) { return reinterpret_cast<const int32_t*>(h_met)[g * 4 + 3]; };
+    const auto p_cnt = [p_met](size_t g) { return reinterpret_cast<const int32_t*>(p_met)[g * 4 + 3]; };
     // The private streams are non-blocking: order them after whatever the caller enqueued on its own stream(s)
     // (agar_reset, agar_step, agar_set_state ...) since the previous host-buffer step.
     if (e->pending) {
@@ -788,11 +864,14 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
         const int sentmask = sentinel_mask(e->p);
         std::atomic<int>* rdy = &ready;
         std::atomic<long long>* ptsc = prof ? e->prof_tsc : nullptr;
+        long long* pfin = e->prof_fin;
+        TakeCounter* take = e->take;
+        for (int i = 0; i < kHostChunks * kMaxWorkers; ++i) take[i].v.store(0, std::memory_order_relaxed);
         job = [=](int w, int nw) {
             DeltaPlan plan[2];
             long long tsc[5] = {0, 0, 0, 0, 0}, t_last = ptsc ? (long long)__rdtsc() : 0;
             auto tick = [&](int slot) { if (ptsc) { const long long t = (long long)__rdtsc(); tsc[slot] += t - t_last; t_last = t; } };
-            auto in_place = [&](size_t g) { return delta && h_cnt[g] <= cap && p_cnt[g] <= cap; };  // (an image copied whole has no list)
+            auto in_place = [&](size_t g) { return delta && h_cnt(g) <= cap && p_cnt(g) <= cap; };  // (an image copied whole has no list)
             for (int k = 0; k < chunks; ++k) {
                 const size_t g0 = (size_t)(N * k / chunks) * A, g1 = (size_t)(N * (k + 1) / chunks) * A;
                 for (int spins = 0;; ++spins) {
@@ -802,26 +881,56 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
                     if ((spins & 1023) == 1023) std::this_thread::yield(); else _mm_pause();
                 }
                 tick(0);
+                // Worker v's list of this chunk is the agents g0 + v, g0 + v + nw, ...; `take[k][v]` counts how many of
+                // them have been taken.  A worker goes through its own list (the same agents every step: their lines are
+                // in its core's L2), then takes from the lists of the others, so that a worker whose core is shared
+                // with something else for a while does not hold the call back (measured: the last worker finished
+                // 2-4x later than the median one).
+                constexpr size_t kEnd = ~(size_t)0;
+                // (taken kTake at a time: the locked add waits for the stores of the agent just written to drain, which
+                // costs ~1 k cycles when paid per agent)
+                constexpr int kTake = 8;
+                int victim = w;
+                size_t gb = 0, ge = 0;  // the agents in hand: gb, gb + nw, ... below ge
+                auto fetch = [&]() -> size_t {
+                    if (gb < ge) { const size_t g = gb; gb += (size_t)nw; return g; }
+                    for (int tries = 0; tries < nw; ++tries) {
+                        const size_t i0 = (size_t)take[k * kMaxWorkers + victim].v.fetch_add(kTake, std::memory_order_relaxed);
+                        const size_t g = g0 + (size_t)victim + (size_t)nw * i0;
+                        if (g < g1) {
+                            const size_t lim = g + (size_t)nw * kTake;
+                            ge = lim < g1 ? lim : g1;
+                            gb = g + (size_t)nw;
+                            return g;
+                        }
+                        victim = victim + 1 == nw ? 0 : victim + 1;
+                    }
+                    return kEnd;
+                };
                 int pi = 0;
-                const size_t gf = g0 + (size_t)w;
-                if (gf < g1 && in_place(gf)) delta_plan(ce->p, p_met + gf * 4, h_met + gf * 4, sentmask, plan[0]);
-                for (size_t g = gf; g < g1; g += (size_t)nw) {
-                    const size_t gn = g + (size_t)nw;  // this worker's next agent: plan it and start its misses now
-                    if (gn < g1 && in_place(gn)) {
+                size_t g = fetch();
+                if (g != kEnd && in_place(g)) delta_plan(ce->p, p_met + g * 4, h_met + g * 4, sentmask, plan[0]);
+                while (g != kEnd) {
+                    const size_t gn = fetch();  // plan the agent after this one and start its misses now
+                    if (gn != kEnd && in_place(gn)) {
                         delta_plan(ce->p, p_met + gn * 4, h_met + gn * 4, sentmask, plan[pi ^ 1]);
                         tick(1);
-                        delta_prefetch(ce->p, h_obs + gn * per_agent, plan[pi ^ 1], p_ent + gn * cap, p_cnt[gn], h_ent + gn * cap, h_cnt[gn]);
+                        delta_prefetch(ce->p, h_obs + gn * per_agent, plan[pi ^ 1], p_ent + gn * cap, p_cnt(gn), h_ent + gn * cap, h_cnt(gn));
                         tick(2);
                     }
-                    const int cnt = h_cnt[g];
+                    const int cnt = h_cnt(g);
                     if (cnt <= cap) {  // (an overflowed list: the calling thread has the image copied whole)
-                        if (in_place(g)) { delta_apply(ce->p, h_obs + g * per_agent, plan[pi], p_ent + g * cap, p_cnt[g], h_ent + g * cap, cnt, h_met + g * 4); tick(3); }
+                        if (in_place(g)) { delta_apply(ce->p, h_obs + g * per_agent, plan[pi], p_ent + g * cap, p_cnt(g), h_ent + g * cap, cnt, h_met + g * 4); tick(3); }
                         else { expand_agent(ce->p, h_obs + g * per_agent, h_ent + g * cap, cnt, h_met + g * 4); tick(4); }
                     }
+                    g = gn;
                     pi ^= 1;
                 }
             }
-            if (ptsc) for (int i = 0; i < 5; ++i) ptsc[i].fetch_add(tsc[i], std::memory_order_relaxed);
+            if (ptsc) {
+                for (int i = 0; i < 5; ++i) ptsc[i].fetch_add(tsc[i], std::memory_order_relaxed);
+                if (w < 64) pfin[w] = (long long)__rdtsc();
+            }
         };
         e->pool->start(job);
         guard.active = true;
@@ -837,9 +946,9 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
         if (int rc = launch(e, a, a1 - a0, st, false)) return rc;
         if (!h_obs) continue;
         const size_t g0 = (size_t)a0 * A, gn = (size_t)(a1 - a0) * A;  // agents of this chunk
-        if (compact) {
+        if (compact) {  // (on the compute stream: beside the next chunk's step kernel, on the copy stream, the lists arrive later - measured)
             obs_compact_kernel<<<(unsigned)gn, 256, 0, st>>>(e->d_obs + g0 * per_agent, (int)per_agent, cap, e->d_entries + g0 * cap,
-                                                             e->d_counts + g0);
+                                                             reinterpret_cast<int32_t*>(e->d_meta + g0 * 4) + 3, 4);
             CUDA_OK(cudaGetLastError());
             e->launches += 1;
         }
@@ -847,10 +956,9 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
         CUDA_OK(cudaStreamWaitEvent(st2, e->host_event, 0));
         if (compact) {
             CUDA_OK(cudaMemcpyAsync(h_ent + g0 * cap, e->d_entries + g0 * cap, gn * cap * sizeof(ObsEntry), cudaMemcpyDeviceToHost, st2));
-            CUDA_OK(cudaMemcpyAsync(h_cnt + g0, e->d_counts + g0, gn * sizeof(int32_t), cudaMemcpyDeviceToHost, st2));
             CUDA_OK(cudaMemcpyAsync(h_met + g0 * 4, e->d_meta + g0 * 4, gn * 4 * sizeof(float), cudaMemcpyDeviceToHost, st2));
             CUDA_OK(cudaEventRecord(e->chunk_done[k], st2));
-            e->last_d2h += (int64_t)(gn * cap * sizeof(ObsEntry) + gn * sizeof(int32_t) + gn * 4 * sizeof(float));
+            e->last_d2h += (int64_t)(gn * cap * sizeof(ObsEntry) + gn * 4 * sizeof(float));
         } else {
             e->last_d2h += (int64_t)((size_t)(a1 - a0) * per_arena * sizeof(float));
             CUDA_OK(cudaMemcpyAsync(h_obs + a0 * per_arena, e->d_obs + a0 * per_arena, (size_t)(a1 - a0) * per_arena * sizeof(float),
@@ -866,15 +974,22 @@ int agar_step_host(AgarEnv* e, const float* h_target_xy, const int32_t* h_act, f
             CUDA_OK(cudaEventSynchronize(e->chunk_done[k]));
             ready.store(k + 1, std::memory_order_release);
             for (size_t g = g0; g < g1; ++g)  // an overflowed list: the image is copied whole (the workers skip the agent)
-                if (h_cnt[g] > cap) {
+                if (h_cnt(g) > cap) {
                     CUDA_OK(cudaMemcpyAsync(h_obs + g * per_agent, e->d_obs + g * per_agent, per_agent * sizeof(float), cudaMemcpyDeviceToHost, st2));
                     e->last_d2h += (int64_t)(per_agent * sizeof(float));
                 }
         }
         lap(1);
+        const long long t_pub = prof ? (long long)__rdtsc() : 0;
         e->pool->wait();
         guard.active = false;
         lap(2);
+        if (prof) {
+            std::vector<long long> f(e->prof_fin, e->prof_fin + std::min(64, e->pool->size()));
+            std::sort(f.begin(), f.end());
+            e->prof_spread[0] += (double)(f.front() - t_pub) / 1e3; e->prof_spread[1] += (double)(f[f.size() / 2] - t_pub) / 1e3;
+            e->prof_spread[2] += (double)(f.back() - t_pub) / 1e3;
+        }
     }
     CUDA_OK(cudaStreamSynchronize(st));
     CUDA_OK(cudaStreamSynchronize(st2));

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) screen_gray_kernel(const uint8_t* __restr
 // grids with its own threads.  One CTA per agent; the order of the pairs is arbitrary (indices are distinct).
 struct ObsEntry { uint32_t idx; float val; };
 __global__ void __launch_bounds__(256) obs_compact_kernel(const float* __restrict__ obs, int floats_per_agent, int cap,
-                                                         ObsEntry* __restrict__ entries, int32_t* __restrict__ counts) {
+                                                         ObsEntry* __restrict__ entries, int32_t* __restrict__ counts, int count_stride) {
     __shared__ int cnt;
     const int tid = threadIdx.x, agent = blockIdx.x;
     if (tid == 0) cnt = 0;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) obs_compact_kernel(const float* __restric
         emit(4u * i, v.x); emit(4u * i + 1u, v.y); emit(4u * i + 2u, v.z); emit(4u * i + 3u, v.w);
     }
     __syncthreads();
-    if (tid == 0) counts[agent] = cnt;  // > cap: the list overflowed and the host copies this agent's image instead
+    if (tid == 0) counts[(size_t)agent * count_stride] = cnt;  // > cap: the list overflowed and the host copies this agent's image instead
 }
 
 // ------------------------------------------------------------------------------ RAM-style features
