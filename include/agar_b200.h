@@ -231,8 +231,11 @@ int agar_events(AgarEnv* env, int32_t* d_events, int32_t* d_counts, void* stream
  * after work enqueued earlier on caller streams through this handle.  For batches of 256 agents
  * or more the dense grids do not cross PCIe: each agent's centroid and occupied bins do (a few KB
  * instead of 48 KB at 3x64x64) and worker threads of the library rebuild the identical float32
- * grids in h_obs (AGAR_HOST_THREADS, default: the process's cores divided by LOCAL_WORLD_SIZE;
- * AGAR_HOST_DENSE=1 restores the plain image copy). */
+ * grids in h_obs (AGAR_HOST_THREADS, default: the process's cores divided by LOCAL_WORLD_SIZE, less
+ * one for the calling thread; the workers are pinned to this rank's share of the process's CPU set
+ * and the calling thread stays on the free core of the share for the duration of the call -
+ * AGAR_HOST_PIN=0 leaves all of them to the scheduler; AGAR_HOST_DENSE=1 restores the plain image
+ * copy). */
 int agar_step_host(AgarEnv* env, const float* h_target_xy, const int32_t* h_act, float* h_obs,
                    float* h_reward, uint8_t* h_done);
 

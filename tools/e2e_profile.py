@@ -15,6 +15,11 @@ import torch  # noqa: E402
 import agarai_b200 as ab  # noqa: E402
 import bench  # noqa: E402
 
+torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))  # (under torchrun: one copy per GPU, all stepping at once)
+WORLD = int(os.environ.get("WORLD_SIZE", 1))
+if WORLD > 1:
+    import torch.distributed as dist
+    dist.init_process_group("gloo")
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 for persistent in (False, True):
@@ -30,10 +35,14 @@ for persistent in (False, True):
     h_r = torch.empty((N, 1), dtype=torch.float32).pin_memory(); h_d = torch.empty((N, 1), dtype=torch.uint8).pin_memory()
     env.host_obs_persistent(persistent)
     env.step_host(h_xy[0].numpy(), h_act[0].numpy(), h_obs.numpy(), h_r.numpy(), h_d.numpy())
+    if WORLD > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for i in range(1, K + 1):
         env.step_host(h_xy[i].numpy(), h_act[i].numpy(), h_obs.numpy(), h_r.numpy(), h_d.numpy())
     dt = time.perf_counter() - t0
-    print(f"persistent={persistent} threads={os.environ.get('AGAR_HOST_THREADS', 'default')}: {K * N / dt / 1e6:.2f} M env-steps/s, {dt / K * 1e3:.3f} ms per step", flush=True)
+    if WORLD > 1:
+        dist.barrier()
+    print(f"rank {os.environ.get('RANK', 0)} persistent={persistent} threads={os.environ.get('AGAR_HOST_THREADS', 'default')}: {K * N / dt / 1e6:.2f} M env-steps/s, {dt / K * 1e3:.3f} ms per step", flush=True)
     sys.stdout.flush()
     env.close()
