@@ -26,7 +26,7 @@ for persistent in (False, True):
     env = ab.BatchedAgarioEnv(ab.default_config(num_arenas=N, **bench.WORLDS["cfg2"]), seed=0, action_config=ab.ActionConfig(8, 1, True, True))
     obs = env.reset()
     g = torch.Generator(device="cuda"); g.manual_seed(0)
-    for _ in range(300):
+    for _ in range(int(os.environ.get("AGE", 300))):
         env.step_discrete(torch.randint(0, env.num_actions, (N, 1), generator=g, device="cuda", dtype=torch.int32), out_obs=obs)
     xy_tab, act_tab = ab.ppo_action_table(ab.ActionConfig(8, 1, True, True))
     idx = np.random.default_rng(0).integers(0, len(act_tab), (K + 1, N, 1))
