@@ -9,6 +9,7 @@ SOURCES = [os.path.join(_HERE, "csrc", "agar_b200.cu")]
 DEPS = SOURCES + [
     os.path.join(_HERE, "csrc", "agar_kernels.cuh"),
     os.path.join(_HERE, "csrc", "agar_features.cuh"),
+    os.path.join(_HERE, "csrc", "agar_host_expand.h"),
     os.path.join(_HERE, "..", "include", "agar_b200.h"),
     os.path.join(_HERE, "..", "include", "agar_spec.h"),
 ]

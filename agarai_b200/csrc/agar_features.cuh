@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "agar_host_expand.h"
 #include "agar_kernels.cuh"
 
 namespace agar {
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256) screen_gray_kernel(const uint8_t* __restr
 // (obs_meta, written by the raster).  This kernel lists the entries of an image that are neither +0.0 nor -1.0 as
 // (index, value) pairs; the host copies the lists (a few KB per agent) instead of the images and rebuilds the dense
 // grids with its own threads.  One CTA per agent; the order of the pairs is arbitrary (indices are distinct).
-struct ObsEntry { uint32_t idx; float val; };
+// (ObsEntry: agar_host_expand.h)
 __global__ void __launch_bounds__(256) obs_compact_kernel(const float* __restrict__ obs, int floats_per_agent, int cap,
                                                          ObsEntry* __restrict__ entries, int32_t* __restrict__ counts, int count_stride) {
     __shared__ int cnt;
