@@ -58,6 +58,11 @@ WORLDS = {
                                 speed_k=8.0, max_foods=16),
     "single_player_no_sentinel_in_others": dict(num_arenas=5, num_agents=1, num_bots=0, num_pellets=200, arena_size=90.0,
                                                 view_size=128.0, grid_size=64, obs_flags=7, speed_k=8.0),
+    # grid sides that are not powers of two (the index -> (channel, row, column) split uses multiply-shift) and the largest one
+    "grid_20": dict(num_arenas=4, num_agents=2, num_bots=3, num_viruses=3, num_pellets=250, arena_size=110.0, view_size=90.0,
+                    grid_size=20, obs_flags=15, start_mass=30.0, speed_k=8.0, auto_reset=1),
+    "grid_128_dqn_like": dict(num_arenas=3, num_agents=1, num_bots=0, num_pellets=30, arena_size=45.0, view_size=30.0, grid_size=128,
+                              obs_flags=15, speed_k=6.0),
     "cfg2": dict(num_arenas=4, num_agents=1, num_bots=25, num_viruses=25, num_pellets=1000, arena_size=500.0, grid_size=64,
                  obs_flags=7, auto_reset=1, max_foods=64),
 }
